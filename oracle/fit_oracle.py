@@ -1,0 +1,110 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (numpy, float32) of the per-iteration allocator fit.
+
+Restates ``PyTorchLogisticRegressionAllocator.update`` (reference src/BidderAllocation.py:29-65)
+together with ``PyTorchLogisticRegression.{predict_item,loss,laplace_approx,update_prior}``
+(src/Models.py:35-48), ``torch.optim.Adam`` (single-tensor path, no amsgrad / weight decay) and
+``torch.optim.lr_scheduler.ReduceLROnPlateau('min', factor=0.5)`` as one explicit state machine.
+torch 1.13.1 is the reference's pin (requirements.txt); torch 2.11.0 is what the golden vectors in
+``tests/golden/fit_*.npz`` were generated with (oracle/make_golden.py).
+
+Only tests / smoke / the bench's CPU-baseline legs may import this module.
+
+Tolerance note: the fit stops where the scheduler says, not at the optimum,
+and the reference moves its own result by ~1e-3 when rows are merely permuted, so parity on fitted
+parameters is |dm| <= 1e-2, q <= 1e-3 rel, stop epoch +-1 %.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+f32 = np.float32
+
+MAX_EPOCHS = 8192 * 2          # BidderAllocation.py:38
+LR0 = 2e-3                     # BidderAllocation.py:39
+BETA1, BETA2, ADAM_EPS = 0.9, 0.999, 1e-8
+PLATEAU_FACTOR, PLATEAU_PATIENCE, PLATEAU_THRESHOLD, PLATEAU_EPS = 0.5, 10, 1e-4, 1e-8
+STOP_AFTER, STOP_WINDOW, STOP_TOL = 1024, 100, 1e-6   # BidderAllocation.py:53
+
+
+def bce_sum32(p, y):
+    """torch.nn.BCELoss(reduction='sum'): log terms clamped at -100 (Models.py:25)."""
+    lp = np.maximum(np.log(p), f32(-100.0))
+    l1p = np.maximum(np.log(f32(1.0) - p), f32(-100.0))
+    return -(y * lp + (f32(1.0) - y) * l1p).astype(f32).sum(dtype=f32)
+
+
+def fit_allocator(X, items, y, m0, q0, m_prev, max_epochs=MAX_EPOCHS, return_losses=False):
+    """One ``allocator.update`` call on the won rows of one agent.
+
+    X [n, Do+1] (context rows incl. the trailing 1), items [n] int, y [n] in {0,1};
+    m0, q0, m_prev [I, Do+1] float32.  Returns dict(m, q, stop_epoch, n_epochs, final_loss, lr).
+    """
+    X = np.asarray(X, f32)
+    items = np.asarray(items, np.int64)
+    y = np.asarray(y, f32)
+    m = np.array(m0, f32, copy=True)
+    q = np.array(q0, f32, copy=True)
+    m_prev = np.asarray(m_prev, f32)
+    n = len(y)
+    out = {"m": m, "q": q, "stop_epoch": -1, "n_epochs": 0, "final_loss": np.nan, "lr": LR0}
+    if n < 2:  # BidderAllocation.py:33
+        return out
+    I, K = m.shape
+    exp_avg = np.zeros_like(m)
+    exp_avg_sq = np.zeros_like(m)
+    lr = LR0
+    best = np.inf
+    bad = 0
+    losses = []
+    onehot = np.zeros((n, I), f32)
+    onehot[np.arange(n), items] = 1
+    stop_epoch = -1
+    for epoch in range(max_epochs):
+        # forward: predict_item (Models.py:37) + loss (Models.py:39-41)
+        z = (X * m[items]).sum(axis=1, dtype=f32)
+        p = (f32(1.0) / (f32(1.0) + np.exp(-z))).astype(f32)
+        diff = (m_prev[:, :-1] - m[:, :-1]).astype(f32)
+        prior = (q[:, :-1] * diff * diff).sum(dtype=f32)
+        loss = f32(0.5) * prior + bce_sum32(p, y)
+        # backward
+        g_row = (p - y).astype(f32)  # d BCE / dz  (away from the log clamp)
+        grad = (onehot.T @ (g_row[:, None] * X)).astype(f32)
+        grad[:, :-1] += (q[:, :-1] * (m[:, :-1] - m_prev[:, :-1])).astype(f32)
+        # Adam step (torch/optim/adam.py _single_tensor_adam)
+        step = epoch + 1
+        exp_avg += (grad - exp_avg) * f32(1 - BETA1)
+        exp_avg_sq *= f32(BETA2)
+        exp_avg_sq += f32(1 - BETA2) * grad * grad
+        bc1 = 1 - BETA1 ** step
+        bc2 = 1 - BETA2 ** step
+        step_size = lr / bc1
+        denom = (np.sqrt(exp_avg_sq) / f32(np.sqrt(bc2)) + f32(ADAM_EPS)).astype(f32)
+        m -= (f32(step_size) * (exp_avg / denom)).astype(f32)
+        losses.append(float(loss))
+        # ReduceLROnPlateau.step(loss)
+        cur = float(loss)
+        if cur < best * (1.0 - PLATEAU_THRESHOLD):
+            best = cur
+            bad = 0
+        else:
+            bad += 1
+        if bad > PLATEAU_PATIENCE:
+            new_lr = lr * PLATEAU_FACTOR
+            if lr - new_lr > PLATEAU_EPS:
+                lr = new_lr
+            bad = 0
+        # early stop (BidderAllocation.py:53-55)
+        if epoch > STOP_AFTER and abs(losses[-STOP_WINDOW] - losses[-1]) < STOP_TOL:
+            stop_epoch = epoch
+            break
+    # Laplace approximation (BidderAllocation.py:58-62, Models.py:43-45) -- note the literal "1 -"
+    for it in range(I):
+        Xi = X[items == it]
+        if len(Xi) == 0:
+            continue
+        P = (f32(1.0) / (f32(1.0) + np.exp(f32(1.0) - Xi @ m[it]))).astype(f32)
+        q[it] += ((P * (f32(1.0) - P))[:, None] * Xi * Xi).sum(axis=0, dtype=f32)
+    out.update(m=m, q=q, stop_epoch=stop_epoch, n_epochs=len(losses), final_loss=losses[-1], lr=lr)
+    if return_losses:
+        out["losses"] = np.asarray(losses)
+    return out

@@ -1,0 +1,61 @@
+"""CPU: the oracle restatement against outputs of the UNMODIFIED reference (tests/golden/*.npz,
+written by oracle/make_golden.py).  This is what pins the oracle (the reference has no tests)."""
+import numpy as np
+import pytest
+
+from oracle import auction_oracle as ao
+from tests import parity
+from tests.conftest import load_golden, round_golden_names
+
+
+@pytest.mark.parametrize("name", round_golden_names())
+def test_round_loop_matches_reference(name):
+    case, inp, ref, met = load_golden(name)
+    rec, m = ao.simulate_rounds(case, inp["ctx"], inp["parts"], inp["u"], inp.get("ts_eps"), inp.get("gamma_z"))
+    ref = dict(ref)
+    ref["winner"] = np.where(ref["won"].any(axis=1), ref["won"].argmax(axis=1), rec["winner"])
+    learnt = bool((case["alloc_kind"] != ao.ALLOC_ORACLE).any())
+    rep = parity.compare_rounds(rec, ref, rec, rtol=parity.RTOL_F64,
+                                est_rtol=parity.RTOL_F32_EST if learnt else parity.RTOL_F64, what=name)
+    if rep["near_tie_rounds"] == 0:
+        parity.compare_metrics(m["acc"], m["revenue"], met, rtol=2e-6 if learnt else 1e-10, what=name)
+
+
+@pytest.mark.parametrize("name", ["rounds_sp_oracle", "rounds_fp_gauss", "rounds_sp_ts", "rounds_fp_pA", "rounds_sp_p1", "rounds_fp_ties"])
+def test_scalar_port_equals_vectorised(name):
+    case, inp, ref, met = load_golden(name)
+    T = min(200, inp["parts"].shape[0])
+    sl = {k: v[:T] for k, v in inp.items()}
+    rec_v, m_v = ao.simulate_rounds(case, sl["ctx"], sl["parts"], sl["u"], sl.get("ts_eps"), sl.get("gamma_z"))
+    rec_s, m_s = ao.simulate_rounds_scalar(case, sl["ctx"], sl["parts"], sl["u"], sl.get("ts_eps"), sl.get("gamma_z"))
+    assert np.array_equal(rec_s["winner"], rec_v["winner"])
+    assert np.array_equal(rec_s["item"], rec_v["item"])
+    assert np.array_equal(rec_s["outcome"], rec_v["outcome"].max(axis=1))
+    np.testing.assert_allclose(m_s["acc"], m_v["acc"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(m_s["revenue"], m_v["revenue"], rtol=1e-12)
+
+
+def test_tie_break_is_lowest_slot():
+    # AuctionAllocation.py:18-23 on exact ties (SURVEY.md section 4 edge cases)
+    bids = np.array([[0.4, 0.9, 0.9], [0.0, 0.0, 0.0], [0.5, 0.5, 0.1]])
+    w, price, second, valid = ao.resolve(bids, ao.MECH_FIRST)
+    assert w.tolist() == [1, 0, 0]
+    assert price.tolist() == [0.9, 0.0, 0.5] and second.tolist() == [0.9, 0.0, 0.5]
+    w, price, second, valid = ao.resolve(bids, ao.MECH_SECOND)
+    assert price.tolist() == [0.9, 0.0, 0.5]
+    # golden: the reference itself on exact ties
+    for name in ("rounds_sp_ties", "rounds_fp_ties"):
+        case, inp, ref, met = load_golden(name)
+        b = ref["bid"]
+        top = b.max(axis=1, keepdims=True)
+        tied = (b == top).sum(axis=1) > 1
+        assert tied.sum() > 20, "fixture should contain exact ties"
+        assert np.array_equal(ref["won"][tied].argmax(axis=1), (b == top)[tied].argmax(axis=1))
+
+
+def test_single_participant_charges_nobody():
+    for name in ("rounds_sp_p1", "rounds_fp_p1"):
+        case, inp, ref, met = load_golden(name)
+        assert ref["won"].sum() == 0 and met["revenue"] == 0.0
+        rec, m = ao.simulate_rounds(case, inp["ctx"], inp["parts"], inp["u"], None, inp.get("gamma_z"))
+        assert rec["won"].sum() == 0 and m["revenue"] == 0.0
