@@ -1,0 +1,307 @@
+// C ABI of libagym (include/agym.h): handle lifetime, configuration, argument checking, dispatch.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "agym_common.cuh"
+
+namespace agym {
+
+static std::string g_create_error;
+
+int set_error(agym_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int check_cuda(agym_handle* h, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return AGYM_OK;
+  return set_error(h, AGYM_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+SimParams make_params(const agym_handle* h) {
+  SimParams p{};
+  const agym_shape& s = h->shape;
+  p.R = s.R; p.A = s.A; p.I = s.I; p.D = s.D; p.Do = s.Do; p.K = h->K; p.P = s.P;
+  p.mechanism = s.mechanism;
+  p.run_offset = s.run_offset;
+  p.embedding_var = s.embedding_var;
+  p.n_items = h->d_n_items; p.alloc_kind = h->d_alloc_kind; p.bidder_kind = h->d_bidder_kind;
+  p.E64 = h->d_E64; p.V64 = h->d_V64; p.E32 = h->d_E32; p.V32 = h->d_V32;
+  p.m = h->m; p.sigma = h->sigma;
+  p.bidder_d = h->bidder_d; p.bidder_w = h->bidder_w;
+  p.acc = h->acc; p.revenue = h->revenue;
+  p.fit_ctx = h->fit_ctx; p.fit_meta = h->fit_meta; p.Tcap = h->Tcap;
+  p.round0 = h->rounds_in_iter;
+  p.run0 = 0; p.n_runs = s.R;
+  return p;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int ready_for_rounds(agym_handle* h, const char* who) {
+  if (!h->agents_set || !h->catalog_set) return set_error(h, AGYM_ERR_STATE, std::string(who) + ": agym_set_agents / agym_set_catalog not called");
+  if (!h->acc || !h->revenue) return set_error(h, AGYM_ERR_STATE, std::string(who) + ": metrics not bound (agym_bind_metrics)");
+  if (h->any_learnt && (!h->m || !h->sigma)) return set_error(h, AGYM_ERR_STATE, std::string(who) + ": learnt allocators need agym_bind_allocator_state");
+  if (h->any_shaded && !h->bidder_d) return set_error(h, AGYM_ERR_STATE, std::string(who) + ": shaded bidders need agym_bind_bidder_state");
+  return AGYM_OK;
+}
+
+}  // namespace agym
+
+using namespace agym;
+
+extern "C" {
+
+int agym_abi_version(void) { return AGYM_ABI_VERSION; }
+
+const char* agym_last_error(const agym_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int agym_create(const agym_shape* shape, int device, agym_handle** out) {
+  if (!shape || !out) return set_error(nullptr, AGYM_ERR_INVALID, "agym_create: null argument");
+  const agym_shape& s = *shape;
+  if (s.R < 1 || s.A < 1 || s.I < 1 || s.D < 1 || s.Do < 0 || s.Do > s.D || s.P < 1 || s.P > s.A)
+    return set_error(nullptr, AGYM_ERR_INVALID, "agym_create: need R,A,I,D >= 1, 0 <= Do <= D, 1 <= P <= A");
+  if (s.A > 4096 || s.I > 4096) return set_error(nullptr, AGYM_ERR_INVALID, "agym_create: A and I are limited to 4096 (fit_meta packing)");
+  if (s.mechanism != AGYM_SECOND_PRICE && s.mechanism != AGYM_FIRST_PRICE) return set_error(nullptr, AGYM_ERR_INVALID, "agym_create: unknown mechanism");
+  if (s.precision != AGYM_FP32 && s.precision != AGYM_FP64) return set_error(nullptr, AGYM_ERR_INVALID, "agym_create: unknown precision");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return set_error(nullptr, AGYM_ERR_CUDA, std::string("agym_create: no CUDA device (") + cudaGetErrorString(e) + "); this engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return set_error(nullptr, AGYM_ERR_INVALID, "agym_create: bad device index");
+  DeviceGuard g(device);
+  agym_handle* h = new agym_handle();
+  h->shape = s;
+  h->device = device;
+  h->K = s.Do + 1;
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+  const size_t nE = (size_t)s.A * s.I * (s.D + 1), nV = (size_t)s.A * s.I;
+  bool ok = cudaMalloc(&h->d_n_items, s.A * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_alloc_kind, s.A * sizeof(int)) == cudaSuccess &&
+            cudaMalloc(&h->d_bidder_kind, s.A * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_E64, nE * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&h->d_V64, nV * sizeof(double)) == cudaSuccess && cudaMalloc(&h->d_E32, nE * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&h->d_V32, nV * sizeof(float)) == cudaSuccess;
+  if (!ok) {
+    set_error(nullptr, AGYM_ERR_CUDA, std::string("agym_create: cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError()));
+    agym_destroy(h);
+    return AGYM_ERR_CUDA;
+  }
+  *out = h;
+  return AGYM_OK;
+}
+
+int agym_destroy(agym_handle* h) {
+  if (!h) return AGYM_OK;
+  DeviceGuard g(h->device);
+  cudaFree(h->d_n_items); cudaFree(h->d_alloc_kind); cudaFree(h->d_bidder_kind);
+  cudaFree(h->d_E64); cudaFree(h->d_V64); cudaFree(h->d_E32); cudaFree(h->d_V32);
+  delete h;
+  return AGYM_OK;
+}
+
+int agym_set_agents(agym_handle* h, const int32_t* n_items, const int32_t* alloc_kind, const int32_t* bidder_kind) {
+  if (!h || !n_items || !alloc_kind || !bidder_kind) return set_error(h, AGYM_ERR_INVALID, "agym_set_agents: null argument");
+  DeviceGuard g(h->device);
+  const int A = h->shape.A;
+  h->any_learnt = h->any_shaded = false;
+  h->max_items = 0;
+  for (int a = 0; a < A; ++a) {
+    if (n_items[a] < 1 || n_items[a] > h->shape.I) return set_error(h, AGYM_ERR_INVALID, "agym_set_agents: n_items out of [1, I]");
+    if (alloc_kind[a] < AGYM_ALLOC_ORACLE || alloc_kind[a] > AGYM_ALLOC_MAP) return set_error(h, AGYM_ERR_INVALID, "agym_set_agents: unknown allocator kind");
+    if (bidder_kind[a] < AGYM_BID_TRUTHFUL || bidder_kind[a] > AGYM_BID_POLICY) return set_error(h, AGYM_ERR_INVALID, "agym_set_agents: unknown bidder kind");
+    h->any_learnt |= alloc_kind[a] != AGYM_ALLOC_ORACLE;
+    h->any_shaded |= bidder_kind[a] != AGYM_BID_TRUTHFUL;
+    if (n_items[a] > h->max_items) h->max_items = n_items[a];
+  }
+  cudaError_t e = cudaMemcpy(h->d_n_items, n_items, A * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_alloc_kind, alloc_kind, A * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_bidder_kind, bidder_kind, A * sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return check_cuda(h, e, "agym_set_agents");
+  h->agents_set = true;
+  return AGYM_OK;
+}
+
+int agym_set_catalog(agym_handle* h, const double* E, const double* V) {
+  if (!h || !E || !V) return set_error(h, AGYM_ERR_INVALID, "agym_set_catalog: null argument");
+  DeviceGuard g(h->device);
+  const agym_shape& s = h->shape;
+  const size_t nE = (size_t)s.A * s.I * (s.D + 1), nV = (size_t)s.A * s.I;
+  std::vector<float> e32(nE), v32(nV);
+  for (size_t i = 0; i < nE; ++i) e32[i] = float(E[i]);
+  for (size_t i = 0; i < nV; ++i) v32[i] = float(V[i]);
+  cudaError_t e = cudaMemcpy(h->d_E64, E, nE * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_V64, V, nV * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_E32, e32.data(), nE * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_V32, v32.data(), nV * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return check_cuda(h, e, "agym_set_catalog");
+  h->catalog_set = true;
+  return AGYM_OK;
+}
+
+int agym_bind_allocator_state(agym_handle* h, float* m, float* q, float* m_prev, float* sigma) {
+  if (!h || !m || !q || !m_prev || !sigma) return set_error(h, AGYM_ERR_INVALID, "agym_bind_allocator_state: null argument");
+  h->m = m; h->q = q; h->m_prev = m_prev; h->sigma = sigma;
+  return AGYM_OK;
+}
+
+int agym_refresh_sigma(agym_handle* h, void* stream) {
+  if (!h) return AGYM_ERR_INVALID;
+  DeviceGuard g(h->device);
+  return launch_refresh_sigma(h, (cudaStream_t)stream);
+}
+
+int agym_bind_bidder_state(agym_handle* h, double* bidder_d, float* bidder_w) {
+  if (!h || !bidder_d || !bidder_w) return set_error(h, AGYM_ERR_INVALID, "agym_bind_bidder_state: null argument");
+  h->bidder_d = bidder_d; h->bidder_w = bidder_w;
+  return AGYM_OK;
+}
+
+int agym_bind_metrics(agym_handle* h, double* acc, double* revenue) {
+  if (!h || !acc || !revenue) return set_error(h, AGYM_ERR_INVALID, "agym_bind_metrics: null argument");
+  h->acc = acc; h->revenue = revenue;
+  return AGYM_OK;
+}
+
+int agym_bind_fit_log(agym_handle* h, float* fit_ctx, uint32_t* fit_meta, int64_t Tcap) {
+  if (!h) return AGYM_ERR_INVALID;
+  if ((fit_ctx == nullptr) != (fit_meta == nullptr) || Tcap < 0) return set_error(h, AGYM_ERR_INVALID, "agym_bind_fit_log: bad arguments");
+  h->fit_ctx = fit_ctx; h->fit_meta = fit_meta; h->Tcap = fit_ctx ? Tcap : 0;
+  return AGYM_OK;
+}
+
+size_t agym_workspace_bytes(const agym_handle* h, int64_t Tcap) { return h ? fit_workspace_bytes(h, Tcap) : 0; }
+
+int agym_bind_workspace(agym_handle* h, void* ws, size_t bytes) {
+  if (!h) return AGYM_ERR_INVALID;
+  h->ws = ws; h->ws_bytes = ws ? bytes : 0;
+  return AGYM_OK;
+}
+
+int64_t agym_rounds_in_iteration(const agym_handle* h) { return h ? h->rounds_in_iter : -1; }
+
+int agym_set_rounds_in_iteration(agym_handle* h, int64_t n) {
+  if (!h) return AGYM_ERR_INVALID;
+  if (n < 0 || (h->fit_ctx && n > h->Tcap)) return set_error(h, AGYM_ERR_INVALID, "agym_set_rounds_in_iteration: out of range");
+  h->rounds_in_iter = n;
+  return AGYM_OK;
+}
+
+static int check_bidders_supported(agym_handle* h) {
+  // kinds >= SEARCH are served by their pre-fit Gaussian behaviour until the bidder fits (K7) land
+  return AGYM_OK;
+}
+
+int agym_simulate_rounds(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, const agym_round_log* log, void* stream) {
+  if (!h) return AGYM_ERR_INVALID;
+  if (T < 0) return set_error(h, AGYM_ERR_INVALID, "agym_simulate_rounds: T < 0");
+  int rc = ready_for_rounds(h, "agym_simulate_rounds");
+  if (rc) return rc;
+  if ((rc = check_bidders_supported(h))) return rc;
+  if (h->any_learnt && h->fit_ctx && h->rounds_in_iter + T > h->Tcap)
+    return set_error(h, AGYM_ERR_INVALID, "agym_simulate_rounds: fit log capacity exceeded (call agym_clear_iteration or bind a larger log)");
+  if (T == 0) return AGYM_OK;
+  DeviceGuard g(h->device);
+  SimParams p = make_params(h);
+  p.T = T; p.seed = seed; p.iter = iter;
+  rc = launch_simulate(h, p, nullptr, log, (cudaStream_t)stream);
+  if (rc == AGYM_OK) h->rounds_in_iter += T;
+  return rc;
+}
+
+int agym_replay_rounds(agym_handle* h, int32_t run0, int32_t n_runs, int64_t T, const agym_replay_inputs* in,
+                       const agym_round_log* log, void* stream) {
+  if (!h || !in) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: null argument");
+  if (run0 < 0 || n_runs < 1 || run0 + n_runs > h->shape.R || T < 0) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: bad run range or T");
+  if (!in->ctx || !in->parts || !in->u) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: ctx, parts and u are required");
+  int rc = ready_for_rounds(h, "agym_replay_rounds");
+  if (rc) return rc;
+  if (h->any_shaded && !in->gamma_z) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: shaded bidders need gamma_z");
+  if (h->fit_ctx && h->rounds_in_iter + T > h->Tcap) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: fit log capacity exceeded");
+  if (T == 0) return AGYM_OK;
+  DeviceGuard g(h->device);
+  SimParams p = make_params(h);
+  p.T = T; p.run0 = run0; p.n_runs = n_runs;
+  rc = launch_simulate(h, p, in, log, (cudaStream_t)stream);
+  if (rc == AGYM_OK && run0 + n_runs == h->shape.R) h->rounds_in_iter += T;  // advance once the last run range was replayed
+  return rc;
+}
+
+int agym_clear_iteration(agym_handle* h, void* stream) {
+  if (!h) return AGYM_ERR_INVALID;
+  if (!h->acc || !h->revenue) return set_error(h, AGYM_ERR_STATE, "agym_clear_iteration: metrics not bound");
+  DeviceGuard g(h->device);
+  const agym_shape& s = h->shape;
+  cudaError_t e = cudaMemsetAsync(h->acc, 0, (size_t)s.R * s.A * kNumMetrics * sizeof(double), (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(h->revenue, 0, (size_t)s.R * sizeof(double), (cudaStream_t)stream);
+  h->rounds_in_iter = 0;
+  return check_cuda(h, e, "agym_clear_iteration");
+}
+
+int agym_update_allocators(agym_handle* h, int32_t fit_mode, int32_t max_epochs, float* fit_info, void* stream) {
+  if (!h) return AGYM_ERR_INVALID;
+  if (fit_mode != AGYM_FIT_ADAM_REF) return set_error(h, AGYM_ERR_INVALID, "agym_update_allocators: unknown fit mode");
+  if (!h->any_learnt) return AGYM_OK;
+  if (!h->m || !h->q || !h->m_prev || !h->sigma) return set_error(h, AGYM_ERR_STATE, "agym_update_allocators: allocator state not bound");
+  if (!h->fit_ctx) return set_error(h, AGYM_ERR_STATE, "agym_update_allocators: fit log not bound");
+  DeviceGuard g(h->device);
+  return launch_update_allocators(h, fit_mode, max_epochs, fit_info, (cudaStream_t)stream);
+}
+
+static int staged_params(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, SimParams* p, const char* who) {
+  if (!h->agents_set || !h->catalog_set) return set_error(h, AGYM_ERR_STATE, std::string(who) + ": configuration incomplete");
+  if (T < 1) return set_error(h, AGYM_ERR_INVALID, std::string(who) + ": T < 1");
+  if (h->shape.A > 256 || h->shape.I > 256) return set_error(h, AGYM_ERR_UNSUPPORTED, std::string(who) + ": staged kernels use uint8 ids (A, I <= 256)");
+  *p = make_params(h);
+  p->T = T; p->seed = seed; p->iter = iter; p->round0 = 0;
+  return AGYM_OK;
+}
+
+int agym_k1_contexts(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, float* ctx, uint8_t* parts, void* stream) {
+  if (!h || !ctx || !parts) return set_error(h, AGYM_ERR_INVALID, "agym_k1_contexts: null argument");
+  SimParams p;
+  int rc = staged_params(h, seed, iter, T, &p, "agym_k1_contexts");
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  return launch_k1(h, p, ctx, parts, (cudaStream_t)stream);
+}
+
+int agym_k2_allocate(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, const float* ctx, const uint8_t* parts,
+                     uint8_t* item, float* est, float* true_ctr, float* best_ev, float* value, void* stream) {
+  if (!h || !ctx || !parts || !item || !est || !true_ctr || !best_ev || !value) return set_error(h, AGYM_ERR_INVALID, "agym_k2_allocate: null argument");
+  SimParams p;
+  int rc = staged_params(h, seed, iter, T, &p, "agym_k2_allocate");
+  if (rc) return rc;
+  if (h->any_learnt && (!h->m || !h->sigma)) return set_error(h, AGYM_ERR_STATE, "agym_k2_allocate: allocator state not bound");
+  DeviceGuard g(h->device);
+  return launch_k2(h, p, ctx, parts, item, est, true_ctr, best_ev, value, (cudaStream_t)stream);
+}
+
+int agym_k3_bids(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, const uint8_t* parts, const float* est,
+                 const float* value, float* bid, float* gamma, float* propensity, void* stream) {
+  if (!h || !parts || !est || !value || !bid) return set_error(h, AGYM_ERR_INVALID, "agym_k3_bids: null argument");
+  SimParams p;
+  int rc = staged_params(h, seed, iter, T, &p, "agym_k3_bids");
+  if (rc) return rc;
+  if (h->any_shaded && !h->bidder_d) return set_error(h, AGYM_ERR_STATE, "agym_k3_bids: bidder state not bound");
+  DeviceGuard g(h->device);
+  return launch_k3(h, p, parts, est, value, bid, gamma, propensity, (cudaStream_t)stream);
+}
+
+int agym_k4_resolve(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, const float* bid, const float* true_ctr,
+                    const float* value, const uint8_t* parts, uint8_t* winner, float* price, float* second,
+                    uint8_t* outcome, int32_t accumulate, void* stream) {
+  if (!h || !bid || !true_ctr || !value || !parts || !winner || !price || !second || !outcome)
+    return set_error(h, AGYM_ERR_INVALID, "agym_k4_resolve: null argument");
+  SimParams p;
+  int rc = staged_params(h, seed, iter, T, &p, "agym_k4_resolve");
+  if (rc) return rc;
+  if (accumulate && (!h->acc || !h->revenue)) return set_error(h, AGYM_ERR_STATE, "agym_k4_resolve: metrics not bound");
+  DeviceGuard g(h->device);
+  return launch_k4(h, p, bid, true_ctr, value, parts, winner, price, second, outcome, accumulate, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+// Shared device/host definitions for libagym (sm_100a).  Internal -- the ABI is include/agym.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "agym.h"
+
+namespace agym {
+
+constexpr int kMaxP = 32;        // participants per round handled by one lane group (P <= group width)
+constexpr int kNumMetrics = AGYM_NUM_METRICS;
+
+// fit_meta packing (agym.h: agym_bind_fit_log)
+constexpr uint32_t kMetaValid = 1u << 31;
+constexpr uint32_t kMetaClick = 1u << 30;
+__host__ __device__ inline uint32_t pack_meta(int agent, int item, bool click) {
+  return kMetaValid | (click ? kMetaClick : 0u) | (uint32_t(agent) << 12) | uint32_t(item);
+}
+__host__ __device__ inline int meta_agent(uint32_t m) { return int((m >> 12) & 0xFFFu); }
+__host__ __device__ inline int meta_item(uint32_t m) { return int(m & 0xFFFu); }
+
+// Everything a round-loop kernel needs, passed by value.
+struct SimParams {
+  int R, A, I, D, Do, K, P, mechanism;
+  int run_offset;
+  double embedding_var;
+  // static per-agent configuration [A]
+  const int* n_items;
+  const int* alloc_kind;
+  const int* bidder_kind;
+  // catalog, both precisions: E [A][I][D+1], V [A][I]
+  const double* E64;
+  const double* V64;
+  const float* E32;
+  const float* V32;
+  // learnt allocator state [R][A][I][K]
+  const float* m;
+  const float* sigma;
+  // bidder state
+  const double* bidder_d;  // [R][A][AGYM_BIDDER_D]
+  const float* bidder_w;   // [R][A][AGYM_BIDDER_W]
+  // accumulators
+  double* acc;      // [R][A][kNumMetrics]
+  double* revenue;  // [R]
+  // winner records for the allocator fit
+  float* fit_ctx;      // [R][Tcap][Do]
+  uint32_t* fit_meta;  // [R][Tcap]
+  long long Tcap;
+  long long round0;  // rounds already simulated in this iteration (append offset and RNG counter base)
+  long long T;       // rounds in this launch
+  int run0, n_runs;  // runs covered by this launch
+  int chunk;         // rounds per CTA
+  // production noise
+  uint64_t seed;
+  int iter;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter-based: key = (seed, run), counter = (round, iter,
+// purpose|slot, index).  Written out here; no curand dependency.
+// ------------------------------------------------------------------------------------------------
+enum Purpose : uint32_t { kPurposeCtx = 0, kPurposePart = 1, kPurposeClick = 2, kPurposeTS = 3, kPurposeGamma = 4, kPurposeGrid = 5 };
+
+struct PhiloxKey {
+  uint32_t k0, k1;
+};
+
+__host__ __device__ inline PhiloxKey make_key(uint64_t seed, uint32_t global_run) {
+  PhiloxKey k;
+  k.k0 = uint32_t(seed) ^ (global_run * 0x9E3779B9u);
+  k.k1 = uint32_t(seed >> 32) ^ (global_run + 0x7F4A7C15u);
+  return k;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key) {
+  uint32_t k0 = key.k0, k1 = key.k1;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// u32 -> (0, 1]
+__device__ __forceinline__ float u32_to_unit_open0(uint32_t x) { return (float(x >> 8) + 1.0f) * (1.0f / 16777216.0f); }
+// u32 -> [0, 1)
+__device__ __forceinline__ float u32_to_unit(uint32_t x) { return float(x >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ double u32x2_to_unit_d(uint32_t hi, uint32_t lo) {
+  return double((uint64_t(hi) << 21) ^ uint64_t(lo >> 11)) * (1.0 / 9007199254740992.0);
+}
+
+// Box-Muller: two u32 -> two standard normals (float).
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = u32_to_unit_open0(a);
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u32_to_unit(b), &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+__device__ __forceinline__ float4 philox_normal4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key) {
+  const uint4 w = philox4x32_10(c0, c1, c2, c3, key);
+  const float2 a = box_muller(w.x, w.y), b = box_muller(w.z, w.w);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// precision policies
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+struct Arith;
+
+template <>
+struct Arith<float> {
+  static constexpr bool kExact = false;
+  __device__ static __forceinline__ float sigmoid(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+  // learnt CTR estimate: float either way
+  __device__ static __forceinline__ float sigmoid32(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+  __device__ static __forceinline__ float ts_weight(float m, float eps, float s) { return fmaf(eps, s, m); }
+  __device__ static __forceinline__ float mac(float w, float x, float acc) { return fmaf(w, x, acc); }
+  __device__ static __forceinline__ float neg_inf() { return -INFINITY; }
+};
+
+template <>
+struct Arith<double> {
+  static constexpr bool kExact = true;
+  __device__ static __forceinline__ double sigmoid(double z) { return 1.0 / (1.0 + exp(-z)); }
+  __device__ static __forceinline__ float sigmoid32(float z) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-z))); }
+  // Models.py:31 -- separately rounded multiply and add, as torch's CPU kernels do
+  __device__ static __forceinline__ float ts_weight(float m, float eps, float s) { return __fadd_rn(m, __fmul_rn(eps, s)); }
+  __device__ static __forceinline__ float mac(float w, float x, float acc) { return __fadd_rn(acc, __fmul_rn(w, x)); }
+  __device__ static __forceinline__ double neg_inf() { return -INFINITY; }
+};
+
+template <typename Real>
+struct Catalog;
+template <>
+struct Catalog<float> {
+  __device__ static __forceinline__ const float* E(const SimParams& p) { return p.E32; }
+  __device__ static __forceinline__ const float* V(const SimParams& p) { return p.V32; }
+};
+template <>
+struct Catalog<double> {
+  __device__ static __forceinline__ const double* E(const SimParams& p) { return p.E64; }
+  __device__ static __forceinline__ const double* V(const SimParams& p) { return p.V64; }
+};
+
+// shuffles for both precisions inside a lane group of width G
+template <int G>
+__device__ __forceinline__ float shfl_xor(float v, int off) { return __shfl_xor_sync(0xffffffffu, v, off, G); }
+template <int G>
+__device__ __forceinline__ double shfl_xor(double v, int off) { return __shfl_xor_sync(0xffffffffu, v, off, G); }
+template <int G>
+__device__ __forceinline__ int shfl_xor(int v, int off) { return __shfl_xor_sync(0xffffffffu, v, off, G); }
+template <int G, typename T>
+__device__ __forceinline__ T shfl_idx(T v, int src) { return __shfl_sync(0xffffffffu, v, src, G); }
+
+}  // namespace agym
+
+// ------------------------------------------------------------------------------------------------
+// host-side handle
+// ------------------------------------------------------------------------------------------------
+struct agym_handle {
+  agym_shape shape;
+  int device;
+  int K;
+  // owned device memory (configuration + catalog, tiny)
+  int* d_n_items = nullptr;
+  int* d_alloc_kind = nullptr;
+  int* d_bidder_kind = nullptr;
+  double* d_E64 = nullptr;
+  double* d_V64 = nullptr;
+  float* d_E32 = nullptr;
+  float* d_V32 = nullptr;
+  bool agents_set = false, catalog_set = false;
+  bool any_learnt = false, any_shaded = false;
+  int max_items = 0;
+  // borrowed
+  float *m = nullptr, *q = nullptr, *m_prev = nullptr, *sigma = nullptr;
+  double* bidder_d = nullptr;
+  float* bidder_w = nullptr;
+  double *acc = nullptr, *revenue = nullptr;
+  float* fit_ctx = nullptr;
+  uint32_t* fit_meta = nullptr;
+  int64_t Tcap = 0;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  int64_t rounds_in_iter = 0;
+  int num_sms = 148;
+  std::string err;
+};
+
+namespace agym {
+int set_error(agym_handle* h, int code, const std::string& msg);
+int check_cuda(agym_handle* h, cudaError_t e, const char* what);
+SimParams make_params(const agym_handle* h);
+
+// kernels' host launchers (one per translation unit)
+int launch_simulate(agym_handle* h, const SimParams& p, const agym_replay_inputs* in, const agym_round_log* log, cudaStream_t s);
+int launch_refresh_sigma(agym_handle* h, cudaStream_t s);
+int launch_update_allocators(agym_handle* h, int fit_mode, int max_epochs, float* fit_info, cudaStream_t s);
+size_t fit_workspace_bytes(const agym_handle* h, int64_t Tcap);
+int launch_k1(agym_handle* h, const SimParams& p, float* ctx, uint8_t* parts, cudaStream_t s);
+int launch_k2(agym_handle* h, const SimParams& p, const float* ctx, const uint8_t* parts, uint8_t* item, float* est,
+              float* true_ctr, float* best_ev, float* value, cudaStream_t s);
+int launch_k3(agym_handle* h, const SimParams& p, const uint8_t* parts, const float* est, const float* value, float* bid,
+              float* gamma, float* propensity, cudaStream_t s);
+int launch_k4(agym_handle* h, const SimParams& p, const float* bid, const float* true_ctr, const float* value,
+              const uint8_t* parts, uint8_t* winner, float* price, float* second, uint8_t* outcome, int accumulate,
+              cudaStream_t s);
+}  // namespace agym

@@ -1,0 +1,230 @@
+// Device building blocks of one auction opportunity, shared by the fused kernel (agym_sim.cu) and the
+// staged kernels (agym_staged.cu) so both produce the same numbers from the same Philox counters.
+#pragma once
+
+#include <limits.h>
+#include <math_constants.h>
+
+#include "agym_common.cuh"
+
+namespace agym {
+
+template <typename Real>
+__device__ __forceinline__ Real pick4(const float4& v, int j) {
+  return Real(j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w);
+}
+
+struct RoundCounter {
+  uint32_t c0, c1;
+  long long round;
+  int iter;
+  __device__ __forceinline__ RoundCounter(long long round_in_iter, int iter_)
+      : c0(uint32_t(round_in_iter)), c1(uint32_t(iter_) ^ (uint32_t(round_in_iter >> 32) << 20)), round(round_in_iter), iter(iter_) {}
+};
+
+// Auction.py:33 -- D normals scaled by embedding_var (used as the std), spread over the group:
+// lane j draws Philox block j = normals 4j..4j+3.
+template <typename Real, int G, int DMAX>
+__device__ __forceinline__ void draw_context(Real (&ctx)[DMAX], int D, Real std, RoundCounter rc, PhiloxKey key, int lane) {
+  const float4 nrm = philox_normal4(rc.c0, rc.c1, kPurposeCtx << 16, uint32_t(lane), key);
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) {
+    const float v = shfl_idx<G>(pick4<float>(nrm, d & 3), (d >> 2) % G);
+    ctx[d] = d < D ? Real(v) * std : Real(0);
+  }
+}
+
+// Per-thread variant of the same draw (staged K1): context component d.
+__device__ __forceinline__ float context_component(int d, RoundCounter rc, PhiloxKey key) {
+  const float4 nrm = philox_normal4(rc.c0, rc.c1, kPurposeCtx << 16, uint32_t(d >> 2), key);
+  return pick4<float>(nrm, d & 3);
+}
+
+// Auction.py:42 -- ordered uniform sample of P agents out of A without replacement.  Slot j takes the
+// r_j-th smallest agent not chosen yet, r_j uniform on [0, A-j) from Philox block j.  Lane s ends up
+// holding slot s's agent.  (numpy's tail-shuffle produces the same distribution, not the same stream.)
+__device__ __forceinline__ int participant_draw(int j, int A, RoundCounter rc, PhiloxKey key) {
+  const uint4 w = philox4x32_10(rc.c0, rc.c1, kPurposePart << 16, uint32_t(j), key);
+  return int(__umulhi(w.x, uint32_t(A - j > 0 ? A - j : 1)));
+}
+
+template <int G>
+__device__ __forceinline__ int draw_participants(int P, int A, RoundCounter rc, PhiloxKey key, int lane) {
+  const int rj = participant_draw(lane, A, rc, key);
+  int mine = 0x7fffffff;
+  const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) / G * G);
+  for (int j = 0; j < P; ++j) {
+    const int x = shfl_idx<G>(rj, j);
+    int xp = x;
+    bool changed;
+    do {  // x-th unchosen agent: fixed point of xp = x + #{chosen <= xp}
+      const unsigned b = __ballot_sync(0xffffffffu, lane < j && mine <= xp) & gmask;
+      const int nx = x + __popc(b);
+      changed = nx != xp;
+      xp = nx;
+    } while (__any_sync(0xffffffffu, changed));
+    if (lane == j) mine = xp;
+  }
+  return lane < P ? mine : 0;
+}
+
+// Per-thread variant (staged K1): writes the P agents to out[0..P).
+__device__ __forceinline__ void draw_participants_thread(int P, int A, RoundCounter rc, PhiloxKey key, int* out) {
+  for (int j = 0; j < P; ++j) {
+    const int x = participant_draw(j, A, rc, key);
+    int xp = x;
+    while (true) {
+      int cnt = 0;
+      for (int i = 0; i < j; ++i) cnt += out[i] <= xp;
+      if (x + cnt == xp) break;
+      xp = x + cnt;
+    }
+    out[j] = xp;
+  }
+}
+
+template <typename Real>
+struct SlotEval {
+  int item;
+  Real est, true_sel, value, best_ev;
+};
+
+// Agent.select_item + the true-CTR bookkeeping of Auction.py:52-53 for the agent in slot s.
+// Lanes of the group stride over the agent's items; the result is uniform across the group.
+template <typename Real, int G, int DMAX, bool kReplay>
+__device__ __forceinline__ SlotEval<Real> eval_slot(const SimParams& p, int run, int a, int s, const Real (&ctx)[DMAX],
+                                                    RoundCounter rc, PhiloxKey key, const float* __restrict__ ts_eps_slot,
+                                                    int lane) {
+  using A_ = Arith<Real>;
+  const int D = p.D, Do = p.Do, K = p.K, I = p.I;
+  const int nI = p.n_items[a];
+  const int akind = p.alloc_kind[a];
+  const Real* __restrict__ Ea = Catalog<Real>::E(p) + (size_t)a * I * (D + 1);
+  const Real* __restrict__ Va = Catalog<Real>::V(p) + (size_t)a * I;
+  const size_t soff = ((size_t)run * p.A + a) * I * K;
+  const float* __restrict__ ma = p.m + soff;
+  const float* __restrict__ sa = p.sigma + soff;
+
+  Real bscore = A_::neg_inf(), btv = A_::neg_inf();
+  int bi = INT_MAX;
+  for (int i = lane; i < nI; i += G) {
+    const Real* __restrict__ e = Ea + (size_t)i * (D + 1);
+    Real z = 0;
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d)
+      if (d < D) z = fma(ctx[d], e[d], z);
+    z += e[D];
+    const Real tc = A_::sigmoid(z);  // Auction.py:52
+    const Real v = Va[i];
+    const Real tv = tc * v;
+    btv = tv > btv ? tv : btv;
+    Real score = tv;  // OracleAllocator: the estimate is the true CTR (BidderAllocation.py:81-82)
+    if (akind != AGYM_ALLOC_ORACLE) {
+      const float* __restrict__ mi = ma + (size_t)i * K;
+      float zl = 0.0f;
+      if (akind == AGYM_ALLOC_TS) {
+        const float* __restrict__ si = sa + (size_t)i * K;
+#pragma unroll
+        for (int kb = 0; kb < (DMAX + 4) / 4; ++kb) {
+          if (kb * 4 < K) {
+            float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!kReplay) nrm = philox_normal4(rc.c0, rc.c1, (kPurposeTS << 16) | uint32_t(s), uint32_t(i * ((DMAX + 4) / 4) + kb), key);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = kb * 4 + j;
+              if (k < K) {
+                const float eps = kReplay ? ts_eps_slot[(size_t)i * K + k] : pick4<float>(nrm, j);
+                const float w = A_::ts_weight(mi[k], eps, si[k]);  // Models.py:31
+                const float x = k < Do ? float(ctx[k < DMAX ? k : 0]) : 1.0f;
+                zl = A_::mac(w, x, zl);
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < DMAX + 1; ++k)
+          if (k < K) zl = A_::mac(mi[k], k < Do ? float(ctx[k < DMAX ? k : 0]) : 1.0f, zl);
+      }
+      score = Real(A_::sigmoid32(zl)) * v;  // Agent.py:33
+    }
+    if (score > bscore) { bscore = score; bi = i; }
+  }
+  // arg-max over the group, lowest item index on ties (np.argmax, Agent.py:35); max of true value
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) {
+    const Real os = shfl_xor<G>(bscore, off);
+    const int oi = shfl_xor<G>(bi, off);
+    const Real ot = shfl_xor<G>(btv, off);
+    if (os > bscore || (os == bscore && oi < bi)) { bscore = os; bi = oi; }
+    btv = ot > btv ? ot : btv;
+  }
+  if (bi == INT_MAX) bi = 0;
+  // chosen item: true CTR and the estimate that is logged and bid on (Agent.py:38-42)
+  const Real* __restrict__ e = Ea + (size_t)bi * (D + 1);
+  Real z = 0;
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d)
+    if (d < D) z = fma(ctx[d], e[d], z);
+  z += e[D];
+  SlotEval<Real> r;
+  r.item = bi;
+  r.true_sel = A_::sigmoid(z);
+  r.est = r.true_sel;
+  if (akind != AGYM_ALLOC_ORACLE) {
+    const float* __restrict__ mi = ma + (size_t)bi * K;
+    float zl = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DMAX + 1; ++k)
+      if (k < K) zl = A_::mac(mi[k], k < Do ? float(ctx[k < DMAX ? k : 0]) : 1.0f, zl);
+    r.est = Real(A_::sigmoid32(zl));
+  }
+  r.value = Va[bi];
+  r.best_ev = btv;
+  return r;
+}
+
+// Bidder.bid (Bidder.py:34-35,47-58,171-179,348-356,455-463).  gamma / prop stay NaN for truthful bidders.
+template <typename Real>
+__device__ __forceinline__ Real shade_bid(const SimParams& p, int run, int a, int s, Real value, Real est, bool replay,
+                                          double gamma_z_replay, RoundCounter rc, PhiloxKey key, Real& gamma, Real& prop) {
+  Real bid = value * est;
+  gamma = Real(CUDART_NAN);
+  prop = Real(CUDART_NAN);
+  const int bkind = p.bidder_kind[a];
+  if (bkind == AGYM_BID_TRUTHFUL) return bid;
+  const double* __restrict__ bd = p.bidder_d + ((size_t)run * p.A + a) * AGYM_BIDDER_D;
+  const Real prev = Real(bd[0]), sg = Real(bd[1]);
+  const int eff = (bkind >= AGYM_BID_SEARCH && bd[2] == 0.0) ? AGYM_BID_GAUSS : bkind;
+  if (eff == AGYM_BID_GAUSS || eff == AGYM_BID_GAUSS_CLIP) {
+    Real zg;
+    if (replay) zg = Real(gamma_z_replay);
+    else zg = Real(philox_normal4(rc.c0, rc.c1, (kPurposeGamma << 16) | uint32_t(s), 0u, key).x);
+    gamma = prev + sg * zg;  // Bidder.py:51,177,354,461
+    if (eff == AGYM_BID_GAUSS_CLIP) {
+      gamma = gamma < Real(0) ? Real(0) : (gamma > Real(1) ? Real(1) : gamma);  // Bidder.py:52-55
+    } else {
+      const Real q_ = (prev - gamma) / sg;
+      prop = exp(-(q_ * q_) / Real(2)) / (sg * Real(2.5066282746310002));  // Bidder.py:178
+    }
+    bid = bid * gamma;
+  }
+  return bid;
+}
+
+// Auction.py:65 -- the click uniform of round t is word (t & 3) of Philox block (t >> 2), so the staged
+// resolution kernel can serve four consecutive rounds from one block.
+__device__ __forceinline__ uint4 click_block(long long round, int iter, PhiloxKey key) {
+  return philox4x32_10(uint32_t(round >> 2), uint32_t(iter) ^ (uint32_t(round >> 34) << 20), kPurposeClick << 16, 0u, key);
+}
+__device__ __forceinline__ uint32_t click_word(RoundCounter rc, PhiloxKey key) {
+  const uint4 w = click_block(rc.round, rc.iter, key);
+  const int j = int(rc.round & 3);
+  return j == 0 ? w.x : j == 1 ? w.y : j == 2 ? w.z : w.w;
+}
+__device__ __forceinline__ float click_uniform_f(RoundCounter rc, PhiloxKey key) { return u32_to_unit(click_word(rc, key)); }
+__device__ __forceinline__ double click_uniform_d(RoundCounter rc, PhiloxKey key) {
+  return (double(click_word(rc, key)) + 0.5) * (1.0 / 4294967296.0);
+}
+
+}  // namespace agym

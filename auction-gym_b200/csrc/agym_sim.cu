@@ -1,0 +1,210 @@
+// K1-K5 fused: one auction opportunity per lane group (reference src/Auction.py:28-74).
+//
+// A lane group (G = 8/16/32 lanes, picked from the catalog width) owns one opportunity:
+//   context draw (Auction.py:33,36) -> participants (Auction.py:42) -> for each participant slot:
+//   item scores over lanes (Agent.py:29-42, BidderAllocation.py:67-68,81-82, Models.py:28-33),
+//   shuffle arg-max with lowest-index tie-break, MAP re-estimate of the chosen item, true CTR and
+//   best expected value (Auction.py:52-53), bid (Bidder.py:34-35,171-179) -> running top-2 with
+//   lowest-slot tie-break (AuctionAllocation.py:18-35) -> Bernoulli click (Auction.py:65) ->
+//   charge / set_price / revenue and every per-agent metric (Agent.py:70-118, main.py:131-148).
+// The same body serves production mode (in-kernel Philox noise) and replay mode (host-drawn noise).
+#include "agym_round.cuh"
+
+namespace agym {
+
+template <typename Real, int G, int DMAX, bool kReplay>
+__global__ void __launch_bounds__(256) sim_kernel(const SimParams p, const agym_replay_inputs in, const agym_round_log log) {
+  using A_ = Arith<Real>;
+  const int lane = threadIdx.x % G, group = threadIdx.x / G, ngroups = blockDim.x / G;
+  const int chunks = int((p.T + p.chunk - 1) / p.chunk);
+  const int rl = blockIdx.x / chunks, ck = blockIdx.x % chunks;
+  const int run = p.run0 + rl;
+  const long long tb = (long long)ck * p.chunk;
+  const long long te = (tb + p.chunk < p.T) ? tb + p.chunk : p.T;
+  const int iters = (p.chunk + ngroups - 1) / ngroups;
+  const int D = p.D, Do = p.Do, P = p.P, A = p.A;
+  const PhiloxKey key = make_key(p.seed, uint32_t(p.run_offset + run));
+
+  for (int it = 0; it < iters; ++it) {
+    const long long t_raw = tb + (long long)it * ngroups + group;
+    const bool active = t_raw < te;
+    const long long t = active ? t_raw : tb;
+    const long long ta = p.round0 + t;             // round index inside the iteration
+    const long long ri = (long long)rl * p.T + t;  // index into per-launch arrays
+    const RoundCounter rc(ta, p.iter);
+
+    // ---- context (Auction.py:33) ----
+    Real ctx[DMAX];
+    if (kReplay) {
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d) ctx[d] = d < D ? Real(in.ctx[ri * D + d]) : Real(0);
+    } else {
+      draw_context<Real, G, DMAX>(ctx, D, Real(p.embedding_var), rc, key, lane);
+    }
+
+    // ---- participants (Auction.py:42): lane s holds the agent of slot s ----
+    int my_agent = 0;
+    if (kReplay) {
+      if (lane < P) my_agent = in.parts[ri * P + lane];
+    } else {
+      my_agent = draw_participants<G>(P, A, rc, key, lane);
+    }
+
+    // ---- bids ----
+    Real best = A_::neg_inf(), second = A_::neg_inf();
+    int wslot = 0;
+    int r_item = 0;
+    Real r_est = 0, r_val = 0, r_bid = 0, r_true = 1, r_bev = 0;
+    Real r_gamma = Real(CUDART_NAN), r_prop = Real(CUDART_NAN);
+
+    for (int s = 0; s < P; ++s) {
+      const int a = shfl_idx<G>(my_agent, s);
+      const float* eps_slot = (kReplay && in.ts_eps) ? in.ts_eps + ((size_t)ri * P + s) * p.I * p.K : nullptr;
+      const SlotEval<Real> ev = eval_slot<Real, G, DMAX, kReplay>(p, run, a, s, ctx, rc, key, eps_slot, lane);
+      Real gamma, prop;
+      const Real bid = shade_bid<Real>(p, run, a, s, ev.value, ev.est, kReplay,
+                                       (kReplay && in.gamma_z) ? in.gamma_z[ri * P + s] : 0.0, rc, key, gamma, prop);
+      // running top-2, strict '>' keeps the lowest slot on ties (AuctionAllocation.py:19,33)
+      if (bid > best) { second = best; best = bid; wslot = s; }
+      else if (bid > second) { second = bid; }
+      if (lane == s) {
+        r_item = ev.item; r_est = ev.est; r_val = ev.value; r_bid = bid; r_true = ev.true_sel; r_bev = ev.best_ev;
+        r_gamma = gamma; r_prop = prop;
+      }
+    }
+
+    // ---- resolution + click (AuctionAllocation.py:18-35, Auction.py:60-65) ----
+    const bool valid = P >= 2;  // P == 1: the reference's price array is empty and nobody is charged
+    const Real price = valid ? (p.mechanism == AGYM_FIRST_PRICE ? best : second) : Real(0);
+    const Real second_p = valid ? second : Real(0);
+    const Real tw = shfl_idx<G>(r_true, wslot);
+    Real u;
+    if (kReplay) u = Real(in.u[ri]);
+    else u = sizeof(Real) == 8 ? Real(click_uniform_d(rc, key)) : Real(click_uniform_f(rc, key));
+    const bool click = valid && (u < tw);
+    const int w_agent = shfl_idx<G>(my_agent, wslot);
+    const int w_item = shfl_idx<G>(r_item, wslot);
+
+    if (active) {
+      // ---- charge / set_price and metric sums (Agent.py:70-118) ----
+      if (lane < P) {
+        const bool won = valid && lane == wslot;
+        const Real tv = r_true * r_val;
+        double* __restrict__ ac = p.acc + ((size_t)run * A + my_agent) * kNumMetrics;
+        if (won) {
+          const Real got = click ? r_val : Real(0);
+          atomicAdd(ac + AGYM_M_NET, double(got - price));
+          atomicAdd(ac + AGYM_M_GROSS, double(got));
+          atomicAdd(ac + AGYM_M_OVERBID_REGRET, double(price - second_p));
+          atomicAdd(ac + AGYM_M_BIAS, double(r_est / r_true));
+          atomicAdd(ac + AGYM_M_NWON, 1.0);
+        } else if (price < tv) {
+          atomicAdd(ac + AGYM_M_UNDERBID_REGRET, double(price - r_bid));
+        }
+        atomicAdd(ac + AGYM_M_ALLOC_REGRET, double(r_bev - tv));
+        atomicAdd(ac + AGYM_M_ESTIM_REGRET, double(r_est * r_val - tv));
+        const Real de = r_true - r_est;
+        atomicAdd(ac + AGYM_M_SQERR, double(de * de));
+        atomicAdd(ac + AGYM_M_NPART, 1.0);
+        atomicAdd(ac + AGYM_M_BEST_EV, double(r_bev));
+        if (r_gamma == r_gamma) atomicAdd(ac + AGYM_M_GAMMA, double(r_gamma));
+      }
+      if (lane == 0 && valid) atomicAdd(p.revenue + run, double(price));  // Auction.py:74
+
+      // ---- winner record for the allocator fit (Agent.py:81-91: won rows only) ----
+      if (p.fit_ctx != nullptr && ta < p.Tcap) {
+        const size_t fi = (size_t)run * p.Tcap + ta;
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k)
+          if (k < Do && lane == (k % G)) p.fit_ctx[fi * Do + k] = float(ctx[k]);
+        if (lane == 0) p.fit_meta[fi] = valid ? pack_meta(w_agent, w_item, click) : 0u;
+      }
+
+      // ---- detailed log (Impression.py:4-31) ----
+      if (lane < P) {
+        const bool won = valid && lane == wslot;
+        const size_t li = (size_t)ri * P + lane;
+        if (log.agent) log.agent[li] = my_agent;
+        if (log.item) log.item[li] = r_item;
+        if (log.est) log.est[li] = double(r_est);
+        if (log.value) log.value[li] = double(r_val);
+        if (log.bid) log.bid[li] = double(r_bid);
+        if (log.true_ctr) log.true_ctr[li] = double(r_true);
+        if (log.best_ev) log.best_ev[li] = double(r_bev);
+        if (log.price) log.price[li] = double(price);
+        if (log.second) log.second[li] = won ? double(second_p) : 0.0;
+        if (log.gamma) log.gamma[li] = double(r_gamma);
+        if (log.propensity) log.propensity[li] = double(r_prop);
+        if (log.outcome) log.outcome[li] = (won && click) ? 1 : 0;
+        if (log.won) log.won[li] = won ? 1 : 0;
+      }
+      if (lane == 0) {
+        if (log.winner) log.winner[ri] = wslot;
+        if (log.ctx) {
+#pragma unroll
+          for (int d = 0; d < DMAX; ++d)
+            if (d < D) log.ctx[ri * D + d] = double(ctx[d]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void refresh_sigma_kernel(const float* __restrict__ q, float* __restrict__ sigma, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sigma[i] = __fdiv_rn(1.0f, __fsqrt_rn(q[i]));  // Models.py:31  1.0/torch.sqrt(q)
+}
+
+int launch_refresh_sigma(agym_handle* h, cudaStream_t s) {
+  if (!h->q || !h->sigma) return set_error(h, AGYM_ERR_STATE, "agym_refresh_sigma: allocator state not bound");
+  const size_t n = (size_t)h->shape.R * h->shape.A * h->shape.I * h->K;
+  refresh_sigma_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(h->q, h->sigma, n);
+  return check_cuda(h, cudaGetLastError(), "refresh_sigma");
+}
+
+template <typename Real, int G, int DMAX>
+static int launch_g(agym_handle* h, const SimParams& p, const agym_replay_inputs* in, const agym_round_log* log, cudaStream_t s) {
+  const int threads = 256;
+  const int ngroups = threads / G;
+  SimParams q = p;
+  // rounds per CTA: 16 per lane group, fewer when the launch is small so the grid still fills the SMs
+  long long chunk = (long long)ngroups * 16;
+  while (chunk > ngroups && ((p.T + chunk - 1) / chunk) * p.n_runs < 4LL * h->num_sms) chunk /= 2;
+  q.chunk = int(chunk);
+  const long long chunks = (p.T + chunk - 1) / chunk;
+  const long long grid = chunks * p.n_runs;
+  if (grid <= 0) return AGYM_OK;
+  if (grid > 0x7fffffffLL) return set_error(h, AGYM_ERR_INVALID, "launch too large: split T");
+  agym_round_log lg = {};
+  if (log) lg = *log;
+  agym_replay_inputs ri = {};
+  if (in) {
+    ri = *in;
+    sim_kernel<Real, G, DMAX, true><<<unsigned(grid), threads, 0, s>>>(q, ri, lg);
+  } else {
+    sim_kernel<Real, G, DMAX, false><<<unsigned(grid), threads, 0, s>>>(q, ri, lg);
+  }
+  return check_cuda(h, cudaGetLastError(), "sim_kernel launch");
+}
+
+template <typename Real, int DMAX>
+static int launch_d(agym_handle* h, const SimParams& p, const agym_replay_inputs* in, const agym_round_log* log, cudaStream_t s) {
+  int G = h->max_items > 16 ? 32 : (h->max_items > 8 ? 16 : 8);
+  while (G < p.P) G *= 2;
+  if (DMAX / 4 > G) G = 32;
+  switch (G) {
+    case 8: return launch_g<Real, 8, DMAX>(h, p, in, log, s);
+    case 16: return launch_g<Real, 16, DMAX>(h, p, in, log, s);
+    default: return launch_g<Real, 32, DMAX>(h, p, in, log, s);
+  }
+}
+
+int launch_simulate(agym_handle* h, const SimParams& p, const agym_replay_inputs* in, const agym_round_log* log, cudaStream_t s) {
+  if (p.P > kMaxP) return set_error(h, AGYM_ERR_UNSUPPORTED, "num_participants_per_round > 32 is not supported yet");
+  if (p.D > 32) return set_error(h, AGYM_ERR_UNSUPPORTED, "embedding_size > 32 is not supported yet");
+  const bool f64 = h->shape.precision == AGYM_FP64;
+  if (p.D <= 8) return f64 ? launch_d<double, 8>(h, p, in, log, s) : launch_d<float, 8>(h, p, in, log, s);
+  return f64 ? launch_d<double, 32>(h, p, in, log, s) : launch_d<float, 32>(h, p, in, log, s);
+}
+
+}  // namespace agym

@@ -1,0 +1,264 @@
+"""Device-resident batch of auction runs: the host side of the C ABI.
+
+``Engine`` owns (through torch) every device buffer the library borrows -- learnt allocator state
+``[R, A, I, K]``, bidder state, metric accumulators, the winner log that feeds the allocator fit -- and
+forwards to ``libagym.so``.  The reference-named classes (``Auction``, ``Agent`` ... in this package)
+and the batched driver (``main.py``) sit on top of it.  torch is used for memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import AgymError, ReplayInputs, RoundLog, Shape
+
+_LOG_DTYPES = {
+    "agent": torch.int32, "item": torch.int32, "est": torch.float64, "value": torch.float64, "bid": torch.float64,
+    "true_ctr": torch.float64, "best_ev": torch.float64, "price": torch.float64, "second": torch.float64,
+    "gamma": torch.float64, "propensity": torch.float64, "outcome": torch.uint8, "won": torch.uint8,
+}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    """R independent runs of one auction configuration on one GPU.
+
+    Parameters mirror what ``parse_config`` / ``instantiate_*`` of the reference produce
+    (src/main.py:24-109): the catalog ``E [A, I, D+1]`` / ``V [A, I]``, per-agent item counts and
+    allocator / bidder kinds (``_lib.ALLOC_*`` / ``_lib.BID_*``).
+    """
+
+    def __init__(self, *, R, A, I, D, Do, P, mechanism, E, V, n_items, alloc_kind, bidder_kind, embedding_var=1.0,
+                 precision=_lib.FP32, device=0, run_offset=0, rounds_capacity=0):
+        if not torch.cuda.is_available():
+            raise AgymError("CUDA device required: the AuctionGym B200 engine has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        self.R, self.A, self.I, self.D, self.Do, self.P = int(R), int(A), int(I), int(D), int(Do), int(P)
+        self.K = self.Do + 1
+        self.mechanism, self.precision = int(mechanism), int(precision)
+        self.shape = Shape(self.R, self.A, self.I, self.D, self.Do, self.P, self.mechanism, self.precision,
+                           int(run_offset), 0, float(embedding_var))
+        self.handle = C.c_void_p()
+        rc = self.lib.agym_create(C.byref(self.shape), device, C.byref(self.handle))
+        if rc != 0:
+            raise AgymError(f"agym_create failed ({rc}): {self.lib.agym_last_error(None).decode()}")
+        self.n_items = np.ascontiguousarray(n_items, np.int32)
+        self.alloc_kind = np.ascontiguousarray(alloc_kind, np.int32)
+        self.bidder_kind = np.ascontiguousarray(bidder_kind, np.int32)
+        assert self.n_items.shape == (self.A,) and self.alloc_kind.shape == (self.A,) and self.bidder_kind.shape == (self.A,)
+        self._check(self.lib.agym_set_agents(self.handle, self.n_items.ctypes.data, self.alloc_kind.ctypes.data,
+                                             self.bidder_kind.ctypes.data))
+        E = np.ascontiguousarray(E, np.float64)
+        V = np.ascontiguousarray(V, np.float64)
+        assert E.shape == (self.A, self.I, self.D + 1) and V.shape == (self.A, self.I), (E.shape, V.shape)
+        self._check(self.lib.agym_set_catalog(self.handle, E.ctypes.data, V.ctypes.data))
+        self.any_learnt = bool((self.alloc_kind != _lib.ALLOC_ORACLE).any())
+        self.any_shaded = bool((self.bidder_kind != _lib.BID_TRUTHFUL).any())
+        dev = self.device
+        # metric accumulators (Agent.net_utility ... / Auction.revenue)
+        self.acc = torch.zeros((self.R, self.A, _lib.NUM_METRICS), dtype=torch.float64, device=dev)
+        self.revenue = torch.zeros((self.R,), dtype=torch.float64, device=dev)
+        self._check(self.lib.agym_bind_metrics(self.handle, _ptr(self.acc), _ptr(self.revenue)))
+        # learnt allocator state (Models.py:21-24): m ~ N(0,1) is drawn by the caller; q = 1
+        st = (self.R, self.A, self.I, self.K)
+        if self.any_learnt:
+            self.m = torch.zeros(st, dtype=torch.float32, device=dev)
+            self.q = torch.ones(st, dtype=torch.float32, device=dev)
+            self.m_prev = torch.zeros(st, dtype=torch.float32, device=dev)
+            self.sigma = torch.ones(st, dtype=torch.float32, device=dev)
+            self._check(self.lib.agym_bind_allocator_state(self.handle, _ptr(self.m), _ptr(self.q), _ptr(self.m_prev), _ptr(self.sigma)))
+        else:
+            self.m = self.q = self.m_prev = self.sigma = None
+        self.bidder_d = torch.zeros((self.R, self.A, _lib.BIDDER_D), dtype=torch.float64, device=dev)
+        self.bidder_w = torch.zeros((self.R, self.A, _lib.BIDDER_W), dtype=torch.float32, device=dev)
+        self._check(self.lib.agym_bind_bidder_state(self.handle, _ptr(self.bidder_d), _ptr(self.bidder_w)))
+        self.fit_ctx = self.fit_meta = self.workspace = None
+        self.rounds_capacity = 0
+        if rounds_capacity:
+            self.reserve_rounds(rounds_capacity)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.agym_last_error(self.handle)
+            raise AgymError(f"libagym error {rc}: {msg.decode() if msg else '?'}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.agym_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reserve_rounds(self, T):
+        """Bind a winner log (fit_ctx / fit_meta) and fit workspace for up to T rounds per iteration."""
+        T = int(T)
+        if T <= self.rounds_capacity:
+            return
+        if not self.any_learnt:
+            self.rounds_capacity = T
+            return
+        if int(self.lib.agym_rounds_in_iteration(self.handle)) != 0:
+            raise AgymError("reserve_rounds: cannot grow the winner log in the middle of an iteration")
+        dev = self.device
+        self.fit_ctx = torch.empty((self.R, T, max(self.Do, 1)), dtype=torch.float32, device=dev)
+        self.fit_meta = torch.zeros((self.R, T), dtype=torch.int32, device=dev)
+        self._check(self.lib.agym_bind_fit_log(self.handle, _ptr(self.fit_ctx), _ptr(self.fit_meta), T))
+        nbytes = int(self.lib.agym_workspace_bytes(self.handle, T))
+        self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        self._check(self.lib.agym_bind_workspace(self.handle, _ptr(self.workspace), nbytes))
+        self.rounds_capacity = T
+
+    # ------------------------------------------------------------------ state
+    def set_allocator_state(self, m, q=None, m_prev=None, non_blocking=False):
+        """Upload learnt state ``[R, A, I, K]`` (numpy or torch, host or device); sigma is refreshed."""
+        if not self.any_learnt:
+            return
+        self.m.copy_(torch.as_tensor(m, dtype=torch.float32).reshape(self.m.shape), non_blocking=non_blocking)
+        if q is not None:
+            self.q.copy_(torch.as_tensor(q, dtype=torch.float32).reshape(self.q.shape), non_blocking=non_blocking)
+        self.m_prev.copy_(self.m if m_prev is None else torch.as_tensor(m_prev, dtype=torch.float32).reshape(self.m.shape),
+                          non_blocking=non_blocking)
+        self._check(self.lib.agym_refresh_sigma(self.handle, self._stream()))
+
+    def set_bidder_state(self, prev_gamma, gamma_sigma, initialised=None, winrate_w=None, policy_w=None):
+        """Per-(run, agent) bidder state; arguments broadcast to ``[R, A]`` (Bidder.py:41-45,159-169,339-346,445-453)."""
+        bd = np.zeros((self.R, self.A, _lib.BIDDER_D), np.float64)
+        bd[..., 0] = np.broadcast_to(np.asarray(prev_gamma, np.float64), (self.R, self.A))
+        bd[..., 1] = np.broadcast_to(np.asarray(gamma_sigma, np.float64), (self.R, self.A))
+        if initialised is not None:
+            bd[..., 2] = np.broadcast_to(np.asarray(initialised, np.float64), (self.R, self.A))
+        self.bidder_d.copy_(torch.from_numpy(bd))
+        if winrate_w is not None or policy_w is not None:
+            bw = np.zeros((self.R, self.A, _lib.BIDDER_W), np.float32)
+            if winrate_w is not None:
+                bw[..., 0:4] = np.broadcast_to(np.asarray(winrate_w, np.float32), (self.R, self.A, 4))
+            if policy_w is not None:
+                bw[..., 4:16] = np.broadcast_to(np.asarray(policy_w, np.float32), (self.R, self.A, 12))
+            self.bidder_w.copy_(torch.from_numpy(bw))
+
+    # ------------------------------------------------------------------ round loop
+    def _alloc_log(self, n_runs, T, fields):
+        log = RoundLog()
+        out = {}
+        for name in fields:
+            if name == "winner":
+                t = torch.empty((n_runs, T), dtype=torch.int32, device=self.device)
+            elif name == "ctx":
+                t = torch.empty((n_runs, T, self.D), dtype=torch.float64, device=self.device)
+            else:
+                t = torch.empty((n_runs, T, self.P), dtype=_LOG_DTYPES[name], device=self.device)
+            out[name] = t
+            setattr(log, name, t.data_ptr())
+        return log, out
+
+    def simulate(self, seed, iteration, T, log_fields=None):
+        """T rounds for every run with in-kernel Philox noise (replaces src/main.py:116-117).
+
+        Returns the dict of device tensors of the detailed log when ``log_fields`` is given."""
+        T = int(T)
+        self.reserve_rounds(int(self.lib.agym_rounds_in_iteration(self.handle)) + T)
+        log, out = (None, None)
+        if log_fields:
+            log, out = self._alloc_log(self.R, T, log_fields)
+        self._check(self.lib.agym_simulate_rounds(self.handle, C.c_uint64(int(seed) & (2**64 - 1)), int(iteration), T,
+                                                  C.byref(log) if log is not None else None, self._stream()))
+        return out
+
+    def replay(self, ctx, parts, u, ts_eps=None, gamma_z=None, grid_u=None, run0=0, log_fields=tuple(_lib._LOG_FIELDS[:-1])):
+        """Replay mode: host-drawn noise for runs ``[run0, run0 + n_runs)``; inputs have a leading run axis."""
+        dev = self.device
+        ctx = torch.as_tensor(np.ascontiguousarray(ctx, np.float64)).to(dev)
+        n_runs, T = ctx.shape[0], ctx.shape[1]
+        parts_t = torch.as_tensor(np.ascontiguousarray(parts, np.int32)).to(dev)
+        u_t = torch.as_tensor(np.ascontiguousarray(u, np.float64)).to(dev)
+        assert ctx.shape == (n_runs, T, self.D) and parts_t.shape == (n_runs, T, self.P) and u_t.shape == (n_runs, T)
+        keep = [ctx, parts_t, u_t]
+        rin = ReplayInputs(ctx.data_ptr(), parts_t.data_ptr(), None, None, None, u_t.data_ptr(), 0, 0)
+        if ts_eps is not None:
+            e = torch.as_tensor(np.ascontiguousarray(ts_eps, np.float32)).to(dev)
+            assert e.shape == (n_runs, T, self.P, self.I, self.K), e.shape
+            keep.append(e)
+            rin.ts_eps = e.data_ptr()
+        if gamma_z is not None:
+            g = torch.as_tensor(np.ascontiguousarray(gamma_z, np.float64)).to(dev)
+            keep.append(g)
+            rin.gamma_z = g.data_ptr()
+        if grid_u is not None:
+            gu = torch.as_tensor(np.ascontiguousarray(grid_u, np.float64)).to(dev)
+            keep.append(gu)
+            rin.grid_u = gu.data_ptr()
+            rin.grid_n = gu.shape[-1]
+        self.reserve_rounds(int(self.lib.agym_rounds_in_iteration(self.handle)) + T)
+        log, out = self._alloc_log(n_runs, T, log_fields)
+        self._check(self.lib.agym_replay_rounds(self.handle, int(run0), int(n_runs), T, C.byref(rin), C.byref(log), self._stream()))
+        torch.cuda.current_stream(dev).synchronize()  # inputs in `keep` must outlive the kernel
+        return out
+
+    def clear_iteration(self):
+        """Agent.clear_utility / clear_logs + Auction.clear_revenue for every run (Agent.py:120-129, Auction.py:76)."""
+        self._check(self.lib.agym_clear_iteration(self.handle, self._stream()))
+
+    @property
+    def rounds_in_iteration(self):
+        return int(self.lib.agym_rounds_in_iteration(self.handle))
+
+    # ------------------------------------------------------------------ updates
+    def update_allocators(self, max_epochs=0, want_info=True):
+        """Agent.update -> allocator.update for every (run, learnt agent) (BidderAllocation.py:29-65)."""
+        if not self.any_learnt:
+            return None
+        info = torch.zeros((self.R, self.A, 4), dtype=torch.float32, device=self.device) if want_info else None
+        self._check(self.lib.agym_update_allocators(self.handle, 0, int(max_epochs), _ptr(info), self._stream()))
+        return info
+
+    # ------------------------------------------------------------------ staged kernels
+    def staged_round(self, seed, iteration, T, accumulate=True):
+        """K1 -> K2 -> K3 -> K4 with the intermediates in HBM; returns them as device tensors."""
+        T = int(T)
+        N, P, dev = self.R * T, self.P, self.device
+        f32, u8 = torch.float32, torch.uint8
+        s = C.c_uint64(int(seed) & (2**64 - 1))
+        b = {
+            "ctx": torch.empty((N, self.D), dtype=f32, device=dev), "parts": torch.empty((N, P), dtype=u8, device=dev),
+            "item": torch.empty((N, P), dtype=u8, device=dev), "est": torch.empty((N, P), dtype=f32, device=dev),
+            "true_ctr": torch.empty((N, P), dtype=f32, device=dev), "best_ev": torch.empty((N, P), dtype=f32, device=dev),
+            "value": torch.empty((N, P), dtype=f32, device=dev), "bid": torch.empty((N, P), dtype=f32, device=dev),
+            "gamma": torch.empty((N, P), dtype=f32, device=dev), "propensity": torch.empty((N, P), dtype=f32, device=dev),
+            "winner": torch.empty((N,), dtype=u8, device=dev), "price": torch.empty((N,), dtype=f32, device=dev),
+            "second": torch.empty((N,), dtype=f32, device=dev), "outcome": torch.empty((N,), dtype=u8, device=dev),
+        }
+        st = self._stream()
+        it = int(iteration)
+        self._check(self.lib.agym_k1_contexts(self.handle, s, it, T, _ptr(b["ctx"]), _ptr(b["parts"]), st))
+        self._check(self.lib.agym_k2_allocate(self.handle, s, it, T, _ptr(b["ctx"]), _ptr(b["parts"]), _ptr(b["item"]),
+                                              _ptr(b["est"]), _ptr(b["true_ctr"]), _ptr(b["best_ev"]), _ptr(b["value"]), st))
+        self._check(self.lib.agym_k3_bids(self.handle, s, it, T, _ptr(b["parts"]), _ptr(b["est"]), _ptr(b["value"]),
+                                          _ptr(b["bid"]), _ptr(b["gamma"]), _ptr(b["propensity"]), st))
+        self.k4_resolve(s, it, T, b, accumulate)
+        return b
+
+    def k4_resolve(self, seed, iteration, T, b, accumulate=True):
+        s = seed if isinstance(seed, C.c_uint64) else C.c_uint64(int(seed) & (2**64 - 1))
+        self._check(self.lib.agym_k4_resolve(self.handle, s, int(iteration), int(T), _ptr(b["bid"]), _ptr(b["true_ctr"]),
+                                             _ptr(b["value"]), _ptr(b["parts"]), _ptr(b["winner"]), _ptr(b["price"]),
+                                             _ptr(b["second"]), _ptr(b["outcome"]), 1 if accumulate else 0, self._stream()))
+
+    # ------------------------------------------------------------------ results
+    def metrics(self):
+        """(acc [R, A, NUM_METRICS], revenue [R]) as numpy arrays (one D2H copy each)."""
+        return self.acc.cpu().numpy(), self.revenue.cpu().numpy()

@@ -1,0 +1,201 @@
+/*
+ * agym.h -- C ABI of the B200-native AuctionGym round-loop engine (libagym.so).
+ *
+ * The reference (soopark0221/auction-gym) is pure Python and has no FFI of its own
+ * (SURVEY.md section 8b): its boundary is the Python class surface
+ *   Auction.simulate_opportunity()            reference src/Auction.py:28-74
+ *   Agent.select_item / bid / charge / update  reference src/Agent.py:29-94
+ *   *.allocate / estimate_CTR / Bidder.bid     reference src/AuctionAllocation.py:18-35,
+ *                                              src/BidderAllocation.py:29-82, src/Bidder.py:28-208
+ * The entry points below are what those Python classes bind (through ctypes, see
+ * auction-gym_b200/_lib.py and INTEGRATION.md).  Conventions:
+ *   - plain C types only; no torch / C++ types cross the boundary;
+ *   - every function returns 0 on success and a negative agym_status otherwise; the message is
+ *     available from agym_last_error(); nothing throws across the ABI;
+ *   - "device pointer" arguments are BORROWED for the lifetime stated; the caller (torch) owns the
+ *     memory.  "host pointer" arguments are small configuration arrays that are copied;
+ *   - all device work is enqueued on the cudaStream_t passed as `void* stream`; no hidden syncs
+ *     except in agym_create / agym_set_* (configuration time);
+ *   - one caller thread per handle (the reference is single-threaded, src/main.py:112-155).
+ *
+ * Shapes:  R runs resident on this device, A agents, I = max items per agent (padded), D =
+ * embedding_size, Do = obs_embedding_size, K = Do+1, P = participants per round, T rounds.
+ */
+#ifndef AGYM_H
+#define AGYM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGYM_ABI_VERSION 1
+
+typedef struct agym_handle agym_handle;
+
+enum agym_status {
+  AGYM_OK = 0,
+  AGYM_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  AGYM_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+  AGYM_ERR_STATE = -3,       /* a required buffer was not bound */
+  AGYM_ERR_UNSUPPORTED = -4  /* feature not built yet (out-of-scope table) */
+};
+
+/* AuctionAllocation.py:10,25 */
+enum agym_mechanism { AGYM_SECOND_PRICE = 0, AGYM_FIRST_PRICE = 1 };
+
+/* BidderAllocation.py:71 (Oracle), :21 with thompson_sampling True / False */
+enum agym_alloc_kind { AGYM_ALLOC_ORACLE = 0, AGYM_ALLOC_TS = 1, AGYM_ALLOC_MAP = 2 };
+
+/* Bid-time behaviour (Bidder.py).  Kinds >= AGYM_BID_SEARCH fall back to AGYM_BID_GAUSS while the
+ * per-(run, agent) `initialised` flag in bidder_d is 0 (Bidder.py:174,351,458). */
+enum agym_bidder_kind {
+  AGYM_BID_TRUTHFUL = 0,    /* TruthfulBidder.bid            Bidder.py:34-35  */
+  AGYM_BID_GAUSS = 1,       /* gamma ~ N(prev, sigma), unclipped   Bidder.py:177,354,461 */
+  AGYM_BID_GAUSS_CLIP = 2,  /* EmpiricalShadedBidder.bid     Bidder.py:47-58  */
+  AGYM_BID_SEARCH = 3,      /* ValueLearningBidder 'search'  Bidder.py:180-196 */
+  AGYM_BID_BANDIT = 4,      /* PolicyLearning / DoublyRobust Bidder.py:357-362,464-470 */
+  AGYM_BID_POLICY = 5       /* ValueLearningBidder 'policy'  Bidder.py:198-203 */
+};
+
+/* Arithmetic of the decision path.
+ *   FP32: contexts, CTRs, bids and prices in float (production throughput mode)
+ *   FP64: the reference's own mix -- float64 everywhere except the learnt CTR estimate, which is
+ *         float32 on a float32 copy of the observed context (BidderAllocation.py:67-68). */
+enum agym_precision { AGYM_FP32 = 0, AGYM_FP64 = 1 };
+
+typedef struct agym_shape {
+  int32_t R, A, I, D, Do, P;
+  int32_t mechanism;   /* agym_mechanism */
+  int32_t precision;   /* agym_precision */
+  int32_t run_offset;  /* global index of this device's first run: RNG keys use run_offset + r, so a
+                          sharded job reproduces the single-device job (main.py:186) */
+  int32_t reserved;
+  double embedding_var; /* used as the STD of the context normal, as Auction.py:33 does */
+} agym_shape;
+
+/* Columns of the per-(run, agent) accumulator block (Agent.py:70-118, main.py:131-148). */
+enum agym_metric {
+  AGYM_M_NET = 0, AGYM_M_GROSS, AGYM_M_ALLOC_REGRET, AGYM_M_ESTIM_REGRET, AGYM_M_OVERBID_REGRET,
+  AGYM_M_UNDERBID_REGRET, AGYM_M_SQERR, AGYM_M_BIAS, AGYM_M_NPART, AGYM_M_NWON, AGYM_M_BEST_EV,
+  AGYM_M_GAMMA, AGYM_NUM_METRICS
+};
+
+/* Per-(run, agent) bidder state. bidder_d: doubles {prev_gamma, gamma_sigma, initialised, reserved};
+ * bidder_w: floats {winrate w[3], b (Models.py:56), policy W1[4], b1[2], w_mu[2], b_mu, w_sigma[2],
+ * b_sigma (Models.py:97-101)}. */
+#define AGYM_BIDDER_D 4
+#define AGYM_BIDDER_W 16
+
+/* Detailed per-(round, slot) log = the SoA form of ImpressionOpportunity (Impression.py:4-31).
+ * Device pointers, each may be NULL (field not wanted).  Layout [n_runs][T][P] unless noted. */
+typedef struct agym_round_log {
+  int32_t* agent;     /* participating agent per slot (Auction.py:42) */
+  int32_t* item;      /* Agent.py:35 */
+  double* est;        /* estimated_CTR logged by Agent.bid (Agent.py:57) */
+  double* value;
+  double* bid;
+  double* true_ctr;   /* Auction.py:53 */
+  double* best_ev;    /* Auction.py:53 */
+  double* price;      /* Agent.py:70-77: winner and losers both log the price */
+  double* second;     /* winner only */
+  double* gamma;      /* NaN for truthful bidders */
+  double* propensity; /* NaN where the reference keeps none */
+  uint8_t* outcome;
+  uint8_t* won;
+  int32_t* winner;    /* [n_runs][T] winning slot */
+  double* ctx;        /* [n_runs][T][D] sampled context without the trailing 1 (production mode) */
+} agym_round_log;
+
+/* Host-drawn noise for replay mode (SURVEY.md section 8c "replay seams").  Device pointers. */
+typedef struct agym_replay_inputs {
+  const double* ctx;      /* [n_runs][T][D]  rng.normal(0, embedding_var, D)      Auction.py:33 */
+  const int32_t* parts;   /* [n_runs][T][P]  rng.choice(A, P, replace=False)      Auction.py:42 */
+  const float* ts_eps;    /* [n_runs][T][P][I][K] standard normals for Models.py:31, or NULL */
+  const double* gamma_z;  /* [n_runs][T][P] standard normals for Bidder.py:177,354,461, or NULL */
+  const double* grid_u;   /* [n_runs][T][P][grid_n] uniforms for Bidder.py:185, or NULL */
+  const double* u;        /* [n_runs][T] click uniforms: outcome = (u < p)        Auction.py:65 */
+  int32_t grid_n;
+  int32_t reserved;
+} agym_replay_inputs;
+
+/* every entry point below is exported even when the library is built with -fvisibility=hidden */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+int agym_abi_version(void);
+const char* agym_last_error(const agym_handle* h); /* h may be NULL: error of the last failed create */
+
+/* ---- lifetime / configuration (host pointers, synchronous) ---- */
+int agym_create(const agym_shape* shape, int device, agym_handle** out);
+int agym_destroy(agym_handle* h);
+/* per-agent static configuration: n_items[A] (<= I), alloc_kind[A], bidder_kind[A]  (main.py:77-95) */
+int agym_set_agents(agym_handle* h, const int32_t* n_items, const int32_t* alloc_kind, const int32_t* bidder_kind);
+/* catalog: E [A][I][D+1] item embeddings with the intercept column, V [A][I] item values (main.py:60-72) */
+int agym_set_catalog(agym_handle* h, const double* E, const double* V);
+
+/* ---- device state owned by the caller (device pointers, borrowed until re-bound / destroy) ---- */
+/* learnt allocator state: m, q, m_prev, sigma = 1/sqrt(q)   each [R][A][I][K] float  (Models.py:21-24) */
+int agym_bind_allocator_state(agym_handle* h, float* m, float* q, float* m_prev, float* sigma);
+int agym_refresh_sigma(agym_handle* h, void* stream);  /* sigma <- 1/sqrt(q) after q was written by the host */
+/* bidder state: bidder_d [R][A][AGYM_BIDDER_D] double, bidder_w [R][A][AGYM_BIDDER_W] float */
+int agym_bind_bidder_state(agym_handle* h, double* bidder_d, float* bidder_w);
+/* accumulators: acc [R][A][AGYM_NUM_METRICS] double, revenue [R] double  (Agent.py:20-21, Auction.py:16) */
+int agym_bind_metrics(agym_handle* h, double* acc, double* revenue);
+/* winner records that feed the allocator fit: fit_ctx [R][Tcap][Do] float, fit_meta [R][Tcap] uint32
+ * (bit 31 valid, bit 30 click, bits 12..23 agent, bits 0..11 item)   (Agent.py:81-91) */
+int agym_bind_fit_log(agym_handle* h, float* fit_ctx, uint32_t* fit_meta, int64_t Tcap);
+size_t agym_workspace_bytes(const agym_handle* h, int64_t Tcap);
+int agym_bind_workspace(agym_handle* h, void* ws, size_t bytes);
+
+/* ---- the round loop (K1-K5 fused) ---- */
+/* T rounds for every resident run with in-kernel Philox4x32-10 noise keyed (seed, run, iter, round).
+ * Appends at round index `rounds_in_iteration`; `log` may be NULL.  Replaces the loop over
+ * Auction.simulate_opportunity at src/main.py:116-117. */
+int agym_simulate_rounds(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, const agym_round_log* log, void* stream);
+/* Same arithmetic, noise served from host-drawn arrays, for runs [run0, run0 + n_runs). */
+int agym_replay_rounds(agym_handle* h, int32_t run0, int32_t n_runs, int64_t T, const agym_replay_inputs* in,
+                       const agym_round_log* log, void* stream);
+int64_t agym_rounds_in_iteration(const agym_handle* h);
+/* For hosts that write fit_ctx / fit_meta themselves (log retention across iterations, Agent.py:124-129;
+ * tests): declare how many rounds of the bound winner log are filled. */
+int agym_set_rounds_in_iteration(agym_handle* h, int64_t n);
+/* Agent.clear_utility / clear_logs + Auction.clear_revenue (Agent.py:120-129, Auction.py:76): zero the
+ * accumulators and rewind the fit log. */
+int agym_clear_iteration(agym_handle* h, void* stream);
+
+/* ---- per-iteration model updates ---- */
+enum agym_fit_mode { AGYM_FIT_ADAM_REF = 0 };
+/* PyTorchLogisticRegressionAllocator.update for every (run, learnt agent) on the winner records of
+ * this iteration (BidderAllocation.py:29-65, Models.py:35-48).  fit_info (device, nullable)
+ * [R][A][4] float: {stop_epoch or -1, epochs run, final loss, rows}. */
+int agym_update_allocators(agym_handle* h, int32_t fit_mode, int32_t max_epochs, float* fit_info, void* stream);
+
+/* ---- staged kernels (intermediates in HBM; used for roofline evidence and isolation tests) ---- */
+/* K1  Auction.py:33,42: contexts [N][D] float and participants [N][P] uint8 for N = n_runs*T opportunities */
+int agym_k1_contexts(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, float* ctx, uint8_t* parts, void* stream);
+/* K2  Agent.py:29-42 + Auction.py:52-53: per participant item (uint8), est, true_ctr, best_ev, value (float) */
+int agym_k2_allocate(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, const float* ctx, const uint8_t* parts,
+                     uint8_t* item, float* est, float* true_ctr, float* best_ev, float* value, void* stream);
+/* K3  Bidder.py:34-35,171-179: bids (float) and, for shaded bidders, gamma / propensity (nullable) */
+int agym_k3_bids(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, const uint8_t* parts, const float* est,
+                 const float* value, float* bid, float* gamma, float* propensity, void* stream);
+/* K4+K5  AuctionAllocation.py:18-35 + Auction.py:65-74 + Agent.py:70-77: segmented top-2 over the P bids
+ * of each opportunity, lowest-slot tie-break, FP/SP price, Bernoulli click, accumulation.
+ * Reads bid, true_ctr, value [N][P] float + parts [N][P] uint8; writes winner [N] uint8, price, second [N]
+ * float, outcome [N] uint8.  `accumulate` != 0 also adds the winner-side metrics and revenue. */
+int agym_k4_resolve(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, const float* bid, const float* true_ctr,
+                    const float* value, const uint8_t* parts, uint8_t* winner, float* price, float* second,
+                    uint8_t* outcome, int32_t accumulate, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGYM_H */
