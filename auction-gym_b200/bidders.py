@@ -1,0 +1,121 @@
+"""Bidders -- same class names and constructor signatures as the reference's src/Bidder.py.
+
+Like the allocators these are descriptors: ``bid`` for a whole batch of opportunities is computed by the
+engine (agym_simulate_rounds / agym_k3_bids); the per-(run, agent) state (prev_gamma, gamma_sigma,
+``model_initialised``, win-rate and policy weights) lives in the engine's ``bidder_d`` / ``bidder_w``.
+"""
+import numpy as np
+
+from . import _lib
+
+
+class Bidder:
+    """Bidder base class (Bidder.py:15-25)."""
+
+    kind = _lib.BID_TRUTHFUL
+    needs_fit = False
+
+    def __init__(self, rng):
+        self.rng = rng
+        self.truthful = False  # Bidder.py:19
+        self._auction = None
+        self._index = None
+
+    def _attach(self, auction, index):
+        self._auction, self._index = auction, index
+
+    def update(self, contexts, values, bids, prices, outcomes, estimated_CTRs, won_mask, iteration, plot, figsize, fontsize, name):
+        if self._auction is not None:
+            self._auction._update_models()
+
+    def clear_logs(self, memory):
+        pass
+
+    # state the engine needs at bid time: (prev_gamma, gamma_sigma)
+    def _gamma_params(self):
+        return 1.0, 0.0
+
+    @property
+    def gammas(self):
+        """Shading factors logged this iteration (Bidder.py:44,164,342,448); needs the detailed log."""
+        if self._auction is None:
+            return []
+        return self._auction._agent_log_column(self._index, "gamma")
+
+    @property
+    def propensities(self):
+        if self._auction is None:
+            return []
+        return self._auction._agent_log_column(self._index, "propensity")
+
+
+class TruthfulBidder(Bidder):
+    """bid = value * estimated CTR (Bidder.py:28-35)."""
+
+    kind = _lib.BID_TRUTHFUL
+
+    def __init__(self, rng):
+        super().__init__(rng)
+        self.truthful = True
+
+    def bid(self, value, context, estimated_CTR):
+        return value * estimated_CTR
+
+
+class _ShadedBidder(Bidder):
+    def __init__(self, rng, gamma_sigma, init_gamma=1.0):
+        super().__init__(rng)
+        self.gamma_sigma = float(gamma_sigma)
+        self.prev_gamma = float(init_gamma)
+
+    def _gamma_params(self):
+        return self.prev_gamma, self.gamma_sigma
+
+
+class EmpiricalShadedBidder(_ShadedBidder):
+    """One global gamma ~ N(prev_gamma, sigma) clipped to [0, 1] (Bidder.py:38-58).  Its bucketised
+    update (Bidder.py:60-147) is not built yet (no shipped config uses it)."""
+
+    kind = _lib.BID_GAUSS_CLIP
+    needs_fit = True
+
+
+class ValueLearningBidder(_ShadedBidder):
+    """Win-rate model + grid search / learnt policy over gamma (Bidder.py:156-333)."""
+
+    needs_fit = True
+
+    def __init__(self, rng, gamma_sigma, init_gamma=1.0, inference="search"):
+        assert inference in ["search", "policy"]
+        super().__init__(rng, gamma_sigma, init_gamma)
+        self.inference = inference
+        self.kind = _lib.BID_SEARCH if inference == "search" else _lib.BID_POLICY
+        self.model_initialised = False
+
+
+class PolicyLearningBidder(_ShadedBidder):
+    """Contextual-bandit policy over gamma trained with REINFORCE / TRPO / PPO losses (Bidder.py:336-439)."""
+
+    kind = _lib.BID_BANDIT
+    needs_fit = True
+
+    def __init__(self, rng, gamma_sigma, loss, init_gamma=1.0):
+        super().__init__(rng, gamma_sigma, init_gamma)
+        self.loss = loss
+        self.model_initialised = False
+
+
+class DoublyRobustBidder(_ShadedBidder):
+    """Win-rate model + doubly-robust policy learning (Bidder.py:442-623)."""
+
+    kind = _lib.BID_BANDIT
+    needs_fit = True
+
+    def __init__(self, rng, gamma_sigma, init_gamma=1.0):
+        super().__init__(rng, gamma_sigma, init_gamma)
+        self.model_initialised = False
+
+
+def gaussian_propensity(prev_gamma, sigma, gamma):
+    """Bidder.py:178 -- density of the logging policy at the drawn gamma."""
+    return np.exp(-((prev_gamma - gamma) / sigma) ** 2 / 2) / (sigma * np.sqrt(2 * np.pi))
