@@ -1,4 +1,5 @@
 // C ABI of libagym (include/agym.h): handle lifetime, configuration, argument checking, dispatch.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -84,7 +85,21 @@ int agym_create(const agym_shape* shape, int device, agym_handle** out) {
   bool ok = cudaMalloc(&h->d_n_items, s.A * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_alloc_kind, s.A * sizeof(int)) == cudaSuccess &&
             cudaMalloc(&h->d_bidder_kind, s.A * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_E64, nE * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->d_V64, nV * sizeof(double)) == cudaSuccess && cudaMalloc(&h->d_E32, nE * sizeof(float)) == cudaSuccess &&
-            cudaMalloc(&h->d_V32, nV * sizeof(float)) == cudaSuccess;
+            cudaMalloc(&h->d_V32, nV * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&h->d_adam_sz0, kAdamTable * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&h->d_adam_bc2s, kAdamTable * sizeof(float)) == cudaSuccess;
+  if (ok) {
+    // torch.optim.Adam's per-step scalars, computed the way torch does (Python floats: beta ** step)
+    std::vector<double> sz0(kAdamTable);
+    std::vector<float> bc2s(kAdamTable);
+    for (int e = 0; e < kAdamTable; ++e) {
+      const double t = double(e + 1);
+      sz0[e] = 2e-3 / (1.0 - std::pow(0.9, t));
+      bc2s[e] = float(std::sqrt(1.0 - std::pow(0.999, t)));
+    }
+    ok = cudaMemcpy(h->d_adam_sz0, sz0.data(), kAdamTable * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(h->d_adam_bc2s, bc2s.data(), kAdamTable * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+  }
   if (!ok) {
     set_error(nullptr, AGYM_ERR_CUDA, std::string("agym_create: cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError()));
     agym_destroy(h);
@@ -99,6 +114,7 @@ int agym_destroy(agym_handle* h) {
   DeviceGuard g(h->device);
   cudaFree(h->d_n_items); cudaFree(h->d_alloc_kind); cudaFree(h->d_bidder_kind);
   cudaFree(h->d_E64); cudaFree(h->d_V64); cudaFree(h->d_E32); cudaFree(h->d_V32);
+  cudaFree(h->d_adam_sz0); cudaFree(h->d_adam_bc2s);
   delete h;
   return AGYM_OK;
 }

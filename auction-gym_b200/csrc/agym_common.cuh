@@ -10,6 +10,7 @@
 
 namespace agym {
 
+constexpr int kAdamTable = 16384;  // BidderAllocation.py:38  epochs = 8192 * 2
 constexpr int kMaxP = 32;        // participants per round handled by one lane group (P <= group width)
 constexpr int kNumMetrics = AGYM_NUM_METRICS;
 
@@ -182,6 +183,8 @@ struct agym_handle {
   double* d_V64 = nullptr;
   float* d_E32 = nullptr;
   float* d_V32 = nullptr;
+  double* d_adam_sz0 = nullptr;  // [kAdamTable] 2e-3 / (1 - 0.9^t), t = epoch + 1 (torch Adam step size at lr 2e-3)
+  float* d_adam_bc2s = nullptr;  // [kAdamTable] sqrt(1 - 0.999^t)
   bool agents_set = false, catalog_set = false;
   bool any_learnt = false, any_shaded = false;
   int max_items = 0;

@@ -1,0 +1,355 @@
+"""bench.py -- auction opportunities/s of the B200 engine on the SP_Truthful_TS-shaped synthetic workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[4]): runs sharded over the GPUs of one box,
+512 runs per GPU (4096 / 8, weak scaling), T = 10 000 rounds per iteration, A = 64 agents x I = 64 items,
+D = 5, Do = 4, P = 2, SecondPrice + TruthfulBidder + learnt Thompson-sampling allocator.
+One step = one iteration of every resident run = T rounds of the fused round-loop kernel (K1-K5) + the
+per-iteration allocator fits (K6, adam_ref: the reference's Adam + plateau scheduler + early-stop state
+machine) + the per-iteration metric read-out.  value = runs * T / step time (whole job, max over ranks).
+
+The JSON line also carries: e2e (same step through the public API with the learnt state and metrics
+crossing PCIe from/to pinned host memory every step), roofline (dominant kernel) + roofline_kernels (every
+kernel, incl. the staged resolution kernel K4 the north star puts the HBM bar on), cpu_baseline (the oracle
+port timed on this box's host cores), clocks, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(A=64, I=64, D=5, Do=4, P=2, T=10000, runs_per_gpu=512)
+METRIC = "auction opportunities/sec"
+UNIT = "opportunities/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--runs-per-gpu", type=int, default=WORKLOAD["runs_per_gpu"])
+    ap.add_argument("--rounds", type=int, default=WORKLOAD["T"])
+    ap.add_argument("--allocator", default="ts", choices=["ts", "oracle"], help="ts = SP_Truthful_TS shape (headline); oracle = SP_Oracle shape")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary staged-kernel roofline measurements")
+    return ap.parse_args()
+
+
+def config_dict(args, world):
+    w = WORKLOAD
+    return {"workload": f"synthetic SP_Truthful_TS shape: {args.runs_per_gpu * world} runs x {args.rounds} rounds/iteration x "
+                        f"{w['A']} agents x {w['I']} items, D={w['D']} Do={w['Do']} P={w['P']}, SecondPrice, TruthfulBidder, "
+                        f"{'learnt Thompson-sampling allocator + adam_ref fits' if args.allocator == 'ts' else 'OracleAllocator (no fits)'}",
+            "runs": args.runs_per_gpu * world, "runs_per_gpu": args.runs_per_gpu, "rounds_per_step": args.rounds,
+            "agents": w["A"], "items": w["I"], "embedding_size": w["D"], "obs_embedding_size": w["Do"],
+            "participants": w["P"], "allocation": "SecondPrice", "allocator": args.allocator, "fit_mode": "adam_ref",
+            "step": "one iteration: T rounds (fused K1-K5) + allocator fits (K6) + metric read-out",
+            "parallelism": f"runs sharded over {world} GPU(s), no data-path collective",
+            "l2": "no flush needed: per-step working set (learnt state + winner log + fit workspace, > 400 MB) exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    """CPU arm: the oracle port on all host cores (the Python reference cannot travel to the GPU box)."""
+    if rank != 0:
+        return
+    from oracle import cpu_bench
+
+    w = WORKLOAD
+    cores = os.cpu_count() or 1
+    workers = max(1, cores)
+    per_step = []
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        warm = i < args.warmup
+        r = cpu_bench.run(w["A"], w["I"], w["D"], w["Do"], w["P"], args.rounds, n_rounds=200 if warm else 600, n_fits=0 if warm else 1,
+                          workers=workers, seed=i)
+        if not warm:
+            per_step.append(r)
+    agg = float(np.mean([r["aggregate_opp_per_s"] for r in per_step]))
+    if args.allocator == "oracle":
+        agg = float(np.mean([r["round_only_per_core"] for r in per_step])) * workers
+    sample = (f"per step and per core: 600 rounds of the scalar port (oracle/auction_oracle.simulate_rounds_scalar) + 1 allocator fit "
+              f"(oracle/fit_oracle) at the bench shape, {workers} processes; opportunities/s = T / (T / round_rate + A * fit_seconds) "
+              f"summed over cores (runs are independent)")
+    line = {"impl": "reference", "metric": METRIC, "value": agg, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(np.mean([r["wall_seconds"] for r in per_step])), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32/f64 (numpy port of the reference's mix)", "data": "synthetic",
+            "config": config_dict(args, world),
+            "cpu_baseline": {"value": agg, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                             "per_core": float(np.mean([r["per_core_opp_per_s"] for r in per_step])),
+                             "round_loop_only_per_core": float(np.mean([r["round_only_per_core"] for r in per_step])),
+                             "fit_seconds": float(np.mean([r["fit_seconds"] for r in per_step])),
+                             "fit_epochs": float(np.mean([r["fit_epochs"] for r in per_step]))},
+            "e2e": {"value": agg, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "total_seconds": time.perf_counter() - t_all}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import auction_gym_b200 as ag
+    from auction_gym_b200 import _lib
+    from oracle import auction_oracle as ao  # catalog sampler only (main.py:60-72); never on the timed path
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = WORKLOAD
+    A, I, D, Do, P, T, R = w["A"], w["I"], w["D"], w["Do"], w["P"], args.rounds, args.runs_per_gpu
+    K = Do + 1
+    learnt = args.allocator == "ts"
+    cat_rng = np.random.default_rng(0)  # the catalog is shared by every run and rank (main.py:60-72)
+    E, V = ao.make_catalog(cat_rng, A, I, D)
+    eng = ag.Engine(R=R, A=A, I=I, D=D, Do=Do, P=P, mechanism=_lib.SECOND_PRICE, E=E, V=V, n_items=[I] * A,
+                    alloc_kind=[_lib.ALLOC_TS if learnt else _lib.ALLOC_ORACLE] * A, bidder_kind=[_lib.BID_TRUTHFUL] * A,
+                    precision=_lib.FP32, device=local_rank, run_offset=rank * R, rounds_capacity=T)
+    g = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    if learnt:
+        m_host = torch.randn((R, A, I, K), generator=g).pin_memory()      # Models.py:22  m ~ N(0, 1)
+        q_host = torch.ones((R, A, I, K)).pin_memory()
+        mp_host = m_host.clone().pin_memory()
+        eng.set_allocator_state(m_host, q_host, mp_host)
+    acc_host = torch.empty((R, A, _lib.NUM_METRICS), dtype=torch.float64).pin_memory()
+    rev_host = torch.empty((R,), dtype=torch.float64).pin_memory()
+    seed = 0
+    stream = torch.cuda.current_stream(dev)
+    ev_pairs = {"rounds": [], "fit": []}
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+
+    def step_device(it, timed):
+        """One iteration with everything resident in HBM; the metric block is read back (1.5 MB) at the end."""
+        eng.clear_iteration()
+        if timed:
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(stream)
+        eng.simulate(seed, it, T)
+        if timed:
+            e1.record(stream)
+        if learnt:
+            eng.update_allocators(want_info=False)
+        if timed:
+            e2.record(stream)
+            ev_pairs["rounds"].append((e0, e1))
+            ev_pairs["fit"].append((e1, e2))
+        acc_host.copy_(eng.acc, non_blocking=True)
+        rev_host.copy_(eng.revenue, non_blocking=True)
+
+    def step_e2e(it):
+        """The same iteration through the public API with HOST buffers: learnt state up, metrics + state down."""
+        if learnt:
+            eng.set_allocator_state(m_host, q_host, mp_host, non_blocking=True)
+        eng.clear_iteration()
+        eng.simulate(seed, it, T)
+        if learnt:
+            eng.update_allocators(want_info=False)
+            m_host.copy_(eng.m, non_blocking=True)
+            q_host.copy_(eng.q, non_blocking=True)
+            mp_host.copy_(eng.m_prev, non_blocking=True)
+        acc_host.copy_(eng.acc, non_blocking=True)
+        rev_host.copy_(eng.revenue, non_blocking=True)
+        stream.synchronize()
+
+    def timed_region(fn, steps, it0):
+        barrier()
+        torch.cuda.synchronize(dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        for i in range(steps):
+            fn(it0 + i)
+        e.record(stream)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up, then the device-resident timed region ----
+    it = 0
+    for _ in range(args.warmup):
+        step_device(it, False)
+        it += 1
+    torch.cuda.synchronize(dev)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms_total = timed_region(lambda i: step_device(i, True), args.steps, it)
+    clk = clocks.stop()
+    it += args.steps
+    opp_per_step = R * T * world
+    value = opp_per_step * args.steps / (ms_total * 1e-3)
+    k_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) if v else 0.0 for k, v in ev_pairs.items()}
+
+    # ---- end to end through host buffers ----
+    step_e2e(it); it += 1  # warm the pinned-copy path
+    ms_e2e = timed_region(step_e2e, args.steps, it)
+    it += args.steps
+    e2e_value = opp_per_step * args.steps / (ms_e2e * 1e-3)
+    state_bytes = 3 * R * A * I * K * 4 if learnt else 0
+    h2d = state_bytes
+    d2h = state_bytes + R * A * _lib.NUM_METRICS * 8 + R * 8
+
+    # ---- roofline bookkeeping ----
+    peak, peak_src = measured_peaks()
+    rows_per_fit = T / A
+    bytes_rounds = R * T * (4 * Do + 4) if learnt else 0          # fused loop: winner record only (20 B/opportunity)
+    bytes_fit = R * T * (4 * Do + 4) + R * A * I * K * 4 * 7     # K6: winner records once + m,q,m_prev read, m,q,m_prev,sigma written
+    kernels = {}
+    if k_ms["rounds"] > 0:
+        kernels["sim_kernel (fused K1-K5)"] = {"ms": k_ms["rounds"], "share": k_ms["rounds"] / (ms_total / args.steps),
+                                                "algorithmic_bytes": bytes_rounds, "achieved_gbs": bytes_rounds / k_ms["rounds"] / 1e6,
+                                                "opportunities_per_s": R * T / k_ms["rounds"] * 1e3,
+                                                "normals_per_s": (R * T * P * I * K / k_ms["rounds"] * 1e3) if learnt else 0.0,
+                                                "bound": "issue (Philox + Box-Muller + exp); HBM traffic is the 20 B/opportunity winner record"}
+    if learnt and k_ms["fit"] > 0:
+        kernels["bucket_kernel + fit_kernel (K6)"] = {"ms": k_ms["fit"], "share": k_ms["fit"] / (ms_total / args.steps),
+                                                       "algorithmic_bytes": bytes_fit, "achieved_gbs": bytes_fit / k_ms["fit"] / 1e6,
+                                                       "fits_per_s": R * A / k_ms["fit"] * 1e3, "rows_per_fit": rows_per_fit,
+                                                       "bound": "latency / issue: sequential Adam epochs on shared-memory-resident rows"}
+    aux = {}
+    if not args.no_aux:
+        # staged resolution kernel K4(+K5) on the same opportunities: HBM-bound, 13P+10 = 36 B/opportunity
+        eng.clear_iteration()
+        b = eng.staged_round(seed, 0, T)
+        for accumulate in (False, True):
+            for _ in range(3):
+                eng.k4_resolve(seed, 0, T, b, accumulate)
+            torch.cuda.synchronize(dev)
+            ts = []
+            for _ in range(10):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(stream); eng.k4_resolve(seed, 0, T, b, accumulate); e.record(stream)
+                torch.cuda.synchronize(dev)
+                ts.append(s.elapsed_time(e))
+            ms4 = float(np.mean(ts))
+            by = R * T * (13 * P + 10)
+            aux["k4_resolve" + ("+accumulate" if accumulate else "")] = {
+                "bound": "hbm", "achieved": by / ms4 / 1e6, "peak": peak, "unit": "GB/s", "frac": by / ms4 / 1e6 / peak,
+                "ms": ms4, "algorithmic_bytes": by, "opportunities_per_s": R * T / ms4 * 1e3, "traffic": None,
+                "note": f"{R * T} opportunities, inputs {by / 1e6:.0f} MB > L2; outside the timed step"}
+        del b
+    dominant = max(kernels.items(), key=lambda kv: kv[1]["ms"])
+    roofline = {"kernel": dominant[0], "bound": "hbm", "achieved": dominant[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": dominant[1]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "note": "the dominant kernel is not HBM-bound (" + dominant[1]["bound"] + "); its algorithmic HBM bytes are tiny by design. "
+                        "The HBM-bound kernel of the path is the staged resolution kernel: see roofline_kernels.k4_resolve"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_bench
+
+        r = cpu_bench.run(A, I, D, Do, P, T, n_rounds=3000, n_fits=6 if learnt else 0, workers=1)
+        cpu_val = r["per_core_opp_per_s"] if learnt else r["round_only_per_core"]
+        cpu = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"3000 rounds of oracle.auction_oracle.simulate_rounds_scalar + {6 if learnt else 0} allocator fits (oracle.fit_oracle, "
+                         f"mean {r['fit_epochs']:.0f} epochs, {r['fit_seconds']:.2f} s each) at the bench shape on one core; "
+                         f"value = T / (T / round_rate + A * fit_seconds)",
+               "round_loop_only": r["round_only_per_core"], "host_cores": os.cpu_count(),
+               "ideal_all_cores": cpu_val * (os.cpu_count() or 1)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config_dict(args, world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": args.steps * (3 if learnt else 1),
+                "round_loop": {"value": R * T * world / k_ms["rounds"] * 1e3 if k_ms["rounds"] else None, "unit": UNIT, "ms": k_ms["rounds"]},
+                "roofline": roofline, "roofline_kernels": {**kernels, **aux}, "cpu_baseline": cpu, "clocks": clk}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
