@@ -1,11 +1,18 @@
 """auction-gym_b200 -- B200-native batched engine for AuctionGym's round loop.
 
 The directory name carries a hyphen (the project's name); import it as ``auction_gym_b200`` (the
-alias package at the repository root) or put this directory's ``src`` on ``sys.path`` to get the
-reference's bare module names (``from Auction import Auction`` ...), as the reference does.
+alias package at the repository root), or put ``auction-gym_b200/src`` on ``sys.path`` to get the
+reference's bare module names (``from Auction import Auction`` ...), exactly as the reference is used.
 """
 from . import _lib  # noqa: F401
 from ._lib import AgymError  # noqa: F401
 from .engine import Engine  # noqa: F401
-
-__all__ = ["Engine", "AgymError", "_lib"]
+from .mechanisms import AllocationMechanism, FirstPrice, SecondPrice  # noqa: F401
+from .allocators import Allocator, LogisticTSAllocator, OracleAllocator, PyTorchLogisticRegressionAllocator  # noqa: F401
+from .bidders import (Bidder, DoublyRobustBidder, EmpiricalShadedBidder, PolicyLearningBidder, TruthfulBidder,  # noqa: F401
+                      ValueLearningBidder)
+from .impression import ImpressionOpportunity  # noqa: F401
+from .agent import Agent  # noqa: F401
+from .auction import Auction  # noqa: F401
+from . import driver  # noqa: F401
+from .driver import instantiate_agents, instantiate_auction, parse_config, run_experiment, shard_runs, write_csvs  # noqa: F401

@@ -1,0 +1,176 @@
+"""``Auction`` with the reference's constructor and methods (src/Auction.py:9-77) on top of the engine.
+
+``simulate_opportunity()`` keeps its one-round-at-a-time meaning (notebooks call it in a Python loop);
+``simulate_rounds(T)`` is the batched form that the driver uses: one fused kernel launch simulates T
+rounds of every resident run.  ``num_runs`` independent replicas of the auction (main.py:186) can live in
+one object; the reference surface then reports arrays of length ``num_runs`` instead of scalars.
+"""
+import numpy as np
+
+from . import _lib
+from .agent import materialise_logs
+from .allocators import OracleAllocator
+from .engine import Engine
+
+_LOG_FIELDS = ("agent", "item", "est", "value", "bid", "true_ctr", "best_ev", "price", "second", "gamma", "propensity",
+               "outcome", "won", "ctx")
+
+
+class Auction:
+    """Base class for auctions (Auction.py:9-26)."""
+
+    def __init__(self, rng, allocation, agents, agent2items, agents2item_values, max_slots, embedding_size, embedding_var,
+                 obs_embedding_size, num_participants_per_round, *, num_runs=1, run_offset=0, device=0, precision=None,
+                 seed=None, init_seed=None, rounds_capacity=0):
+        if max_slots != 1:
+            raise NotImplementedError("multi-slot auctions are not supported (src/main.py:36-37 says the same of the reference)")
+        self.rng = rng
+        self.allocation = allocation
+        self.agents = agents
+        self.max_slots = max_slots
+        self.agent2items = agent2items
+        self.agents2item_values = agents2item_values
+        self.embedding_size = embedding_size
+        self.embedding_var = embedding_var
+        self.obs_embedding_size = obs_embedding_size
+        self.num_participants_per_round = num_participants_per_round
+        self.num_runs = int(num_runs)
+        self.run_offset = int(run_offset)
+        self.device = device
+        self.precision = _lib.FP32 if precision is None else precision
+        if seed is None:
+            seed = int(rng.integers(0, 2**62)) if hasattr(rng, "integers") and hasattr(rng, "bit_generator") else 0
+        self.seed = int(seed)
+        self.init_seed = self.seed if init_seed is None else int(init_seed)
+        self.iteration = 0
+        self.engine = None
+        self._rounds_capacity = int(rounds_capacity)
+        self._models_updated = False
+        self._cleared = set()
+        self._log_chunks = []   # detailed log of run 0 for the current iteration (list of dicts of numpy arrays)
+        self._log_cache = None
+        for i, ag in enumerate(self.agents):
+            ag._attach(self, i)
+
+    # ------------------------------------------------------------------ engine construction
+    def _build(self):
+        A = len(self.agents)
+        D, Do = int(self.embedding_size), int(self.obs_embedding_size)
+        n_items = np.array([int(ag.num_items) for ag in self.agents], np.int32)
+        I = int(n_items.max())
+        E = np.zeros((A, I, D + 1))
+        V = np.ones((A, I))
+        for a, ag in enumerate(self.agents):
+            e = np.asarray(self.agent2items[ag.name], np.float64)
+            if e.shape != (n_items[a], D + 1):
+                raise ValueError(f"item embeddings of {ag.name!r} have shape {e.shape}, expected {(n_items[a], D + 1)}")
+            E[a, :n_items[a]] = e
+            V[a, :n_items[a]] = np.asarray(self.agents2item_values[ag.name], np.float64)
+        eng = Engine(R=self.num_runs, A=A, I=I, D=D, Do=Do, P=int(self.num_participants_per_round),
+                     mechanism=self.allocation.code, E=E, V=V, n_items=n_items,
+                     alloc_kind=[ag.allocator.kind for ag in self.agents], bidder_kind=[ag.bidder.kind for ag in self.agents],
+                     embedding_var=float(self.embedding_var), precision=self.precision, device=self.device,
+                     run_offset=self.run_offset, rounds_capacity=self._rounds_capacity)
+        if eng.any_learnt:
+            m = np.zeros((self.num_runs, A, I, Do + 1), np.float32)
+            q = np.ones_like(m)
+            for r in range(self.num_runs):
+                # one independent initialisation per run (the reference re-instantiates its agents per run, main.py:188)
+                rr = np.random.default_rng([self.init_seed, self.run_offset + r, 0x6d30]) if self.num_runs > 1 or self.run_offset else None
+                for a, ag in enumerate(self.agents):
+                    if isinstance(ag.allocator, OracleAllocator):
+                        continue
+                    if ag.allocator.embedding_size != Do:
+                        raise ValueError(f"{ag.name!r}: allocator embedding_size {ag.allocator.embedding_size} != obs_embedding_size {Do}")
+                    m[r, a, :n_items[a]] = ag.allocator._init_m if rr is None else rr.standard_normal((n_items[a], Do + 1))
+            eng.set_allocator_state(m, q)
+        if eng.any_shaded:
+            pg = np.array([ag.bidder._gamma_params()[0] for ag in self.agents])
+            sg = np.array([ag.bidder._gamma_params()[1] for ag in self.agents])
+            eng.set_bidder_state(pg[None, :], sg[None, :])
+        self.engine = eng
+        self.D_ctx = [D if isinstance(ag.allocator, OracleAllocator) else Do for ag in self.agents]  # Auction.py:46-49
+
+    # ------------------------------------------------------------------ round loop
+    def simulate_opportunity(self):
+        """One auction round (Auction.py:28-74) for every resident run; the detailed log is kept."""
+        self.simulate_rounds(1, keep_logs=True)
+
+    def simulate_rounds(self, T, keep_logs=False):
+        """T rounds in one fused launch (replaces the Python loop at src/main.py:116-117)."""
+        if self.engine is None:
+            self._build()
+        if self._cleared:  # an iteration boundary was only partly crossed (some agents cleared their logs, not all)
+            if len(self._cleared) != len(self.agents):
+                raise NotImplementedError("clear_logs() must be called for every agent before the next round "
+                                          "(per-agent log retention is not supported)")
+        self._models_updated = False
+        out = self.engine.simulate(self.seed, self.iteration, int(T), _LOG_FIELDS if keep_logs else None)
+        if keep_logs:
+            self._log_chunks.append({k: v[0].cpu().numpy() for k, v in out.items()})
+            self._log_cache = None
+
+    @property
+    def revenue(self):  # Auction.py:16,74
+        if self.engine is None:
+            return 0.0
+        v = self.engine.revenue.cpu().numpy()
+        return float(v[0]) if len(v) == 1 else v
+
+    @revenue.setter
+    def revenue(self, value):
+        if self.engine is not None:
+            self.engine.revenue.fill_(float(value))
+
+    def clear_revenue(self):  # Auction.py:76-77
+        if self.engine is not None:
+            self.engine.revenue.zero_()
+
+    # ------------------------------------------------------------------ per-iteration model updates
+    def _update_models(self):
+        if self._models_updated or self.engine is None:
+            return
+        unsupported = sorted({type(ag.bidder).__name__ for ag in self.agents if ag.bidder.needs_fit})
+        if unsupported:
+            raise _lib.AgymError(f"bidder update for {unsupported} (K7, src/Bidder.py:60-147,210-325,369-431,477-615) is not built yet; "
+                                 "see DESIGN.md 'not yet built'")
+        self.engine.update_allocators(want_info=False)
+        self._models_updated = True
+
+    # ------------------------------------------------------------------ logs
+    def _log_columns(self):
+        if self._log_cache is None and self._log_chunks:
+            self._log_cache = {k: np.concatenate([c[k] for c in self._log_chunks], axis=0) for k in self._log_chunks[0]}
+        return self._log_cache
+
+    def _agent_logs(self, index):
+        cols = self._log_columns()
+        return [] if cols is None else materialise_logs(cols, index, self.D_ctx)
+
+    def _agent_log_column(self, index, name):
+        cols = self._log_columns()
+        if cols is None:
+            return []
+        return list(cols[name][cols["agent"] == index])
+
+    def _clear_agent_logs(self, index):
+        if self.engine is None:
+            return
+        keep = [_lib.M_NET, _lib.M_GROSS]
+        cols = [c for c in range(_lib.NUM_METRICS) if c not in keep]
+        self.engine.acc[:, index, cols] = 0.0
+        self._cleared.add(index)
+        if len(self._cleared) == len(self.agents):  # every agent crossed the iteration boundary
+            self.engine._check(self.engine.lib.agym_set_rounds_in_iteration(self.engine.handle, 0))
+            self._log_chunks, self._log_cache = [], None
+            self._cleared = set()
+            self.iteration += 1
+
+    def end_iteration(self):
+        """Batched equivalent of main.py:151-155 for all agents: clear utilities, logs and revenue."""
+        if self.engine is None:
+            return
+        self.engine.clear_iteration()
+        self._log_chunks, self._log_cache = [], None
+        self._cleared = set()
+        self.iteration += 1

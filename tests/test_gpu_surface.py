@@ -1,0 +1,120 @@
+"""GPU: the reference-named Python surface (Auction / Agent / parse_config / instantiate_* / CSV driver) on the engine."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpu():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _small_config(tmp_path, name, **over):
+    cfg = json.load(open(os.path.join(ROOT, "config", name + ".json")))
+    cfg.update(over)
+    cfg["output_dir"] = str(tmp_path / "out") + "/"
+    p = tmp_path / f"{name}.json"
+    json.dump(cfg, open(p, "w"))
+    return str(p)
+
+
+def test_one_round_at_a_time_like_the_notebooks(tmp_path):
+    _need_gpu()
+    import auction_gym_b200 as ag
+    from auction_gym_b200 import _lib
+
+    path = _small_config(tmp_path, "SP_Oracle")
+    rng, config, agent_configs, E, V, num_runs, max_slots, D, var, Do = ag.parse_config(path)
+    agents = ag.instantiate_agents(rng, agent_configs, V, E)
+    auction, num_iter, rounds_per_iter, output_dir = ag.instantiate_auction(rng, config, E, V, agents, max_slots, D, var, Do, precision=_lib.FP64)
+    for _ in range(40):
+        auction.simulate_opportunity()  # notebook cell 4 / main.py:117
+    logs = [ag_.logs for ag_ in auction.agents]
+    assert sum(len(l) for l in logs) == 40 * config["num_participants_per_round"]
+    won = [o for l in logs for o in l if o.won]
+    assert len(won) == 40
+    assert auction.revenue == pytest.approx(sum(o.price for o in won), rel=1e-12)
+    for agent in auction.agents:
+        l = agent.logs
+        assert agent.net_utility == pytest.approx(sum(o.value * o.outcome - o.price for o in l if o.won), rel=1e-12, abs=1e-12)
+        assert agent.gross_utility == pytest.approx(sum(o.value * o.outcome for o in l if o.won), rel=1e-12, abs=1e-12)
+        assert agent.get_allocation_regret() == pytest.approx(sum(o.best_expected_value - o.true_CTR * o.value for o in l), abs=1e-12)
+        assert agent.get_overbid_regret() == 0.0  # second price
+        for o in l:
+            assert o.context.shape == (D + 1,) and o.context[-1] == 1.0   # Oracle agents see the true context
+            assert o.estimated_CTR == pytest.approx(o.true_CTR, rel=1e-12) and o.bid == pytest.approx(o.value * o.estimated_CTR, rel=1e-12)
+            # the chosen item is the arg-max of true CTR x value for this agent (Agent.py:33-35)
+            ctr = 1 / (1 + np.exp(-(E[agent.name] @ o.context)))
+            assert o.item == int(np.argmax(ctr * V[agent.name])) and o.best_expected_value == pytest.approx(np.max(ctr * V[agent.name]), rel=1e-12)
+        agent.update(iteration=0)
+        agent.clear_utility()
+        agent.clear_logs()
+        assert agent.net_utility == 0.0 and agent.logs == []
+    auction.clear_revenue()
+    assert auction.revenue == 0.0 and auction.iteration == 1
+    auction.simulate_opportunity()
+    assert sum(len(a.logs) for a in auction.agents) == config["num_participants_per_round"]
+    auction.engine.close()
+
+
+def test_batched_experiment_writes_the_reference_csvs(tmp_path):
+    _need_gpu()
+    import pandas as pd
+
+    import auction_gym_b200 as ag
+    from oracle import auction_oracle as ao
+
+    path = _small_config(tmp_path, "SP_Oracle", num_runs=16, num_iter=3, rounds_per_iter=2000)
+    result = ag.run_experiment(path)
+    assert result["metrics"].shape == (16, 3, 6, 10) and result["revenue"].shape == (16, 3)
+    out = ag.write_csvs(result)
+    res = pd.read_csv(os.path.join(out, "results_2000_rounds_3_iters_16_runs_4_emb_of_5.csv"))
+    rev = res[res["Measure Name"] == "Auction Revenue"]["Measure"].values
+    np.testing.assert_allclose(np.sort(rev), np.sort(result["revenue"].ravel()))
+    # distribution-level check against the oracle with numpy-drawn noise on the same catalog
+    rng, config, agent_configs, E, V, *_ = ag.parse_config(path)
+    names = [ac["name"] for ac in agent_configs]
+    case = {"A": 6, "I": 12, "D": 5, "Do": 4, "P": 2, "mechanism": ao.MECH_SECOND, "embedding_var": 1.0, "n_items": np.full(6, 12),
+            "E": np.stack([E[n] for n in names]), "V": np.stack([V[n] for n in names]), "alloc_kind": np.zeros(6, int),
+            "bidder_kind": np.zeros(6, int), "bidder_f": np.zeros((6, 4))}
+    r2 = np.random.default_rng(5)
+    ref_rev = []
+    for _ in range(24):
+        nz = ao.draw_replay_inputs(r2, 2000, 6, 2, 5)
+        ref_rev.append(ao.simulate_rounds(case, nz["ctx"], nz["parts"], nz["u"])[1]["revenue"])
+    ref_rev, got = np.asarray(ref_rev), result["revenue"].ravel()
+    se = np.sqrt(ref_rev.var(ddof=1) / len(ref_rev) + got.var(ddof=1) / len(got))
+    assert abs(ref_rev.mean() - got.mean()) < 5 * se
+    # second price + truthful: no overbid / underbid regret
+    assert np.all(result["metrics"][..., 4] == 0) and np.all(result["metrics"][..., 5] == 0)
+
+
+def test_learning_config_improves_over_iterations(tmp_path):
+    _need_gpu()
+    import auction_gym_b200 as ag
+
+    path = _small_config(tmp_path, "SP_Truthful_TS", num_runs=8, num_iter=4, rounds_per_iter=4000)
+    result = ag.run_experiment(path)
+    m = result["metrics"]  # [R, N, A, 10]
+    rmse = m[..., 6].mean(axis=(0, 2))
+    welfare = m[..., 1].sum(axis=2).mean(axis=0)
+    assert rmse[-1] < 0.5 * rmse[0], rmse         # the CTR model learns (reference: CTR RMSE curve falls)
+    assert welfare[-1] > welfare[0], welfare       # welfare rises as allocation improves
+    assert np.isfinite(m[..., :7]).all()
+
+
+def test_unbuilt_bidder_fits_fail_loudly(tmp_path):
+    _need_gpu()
+    import auction_gym_b200 as ag
+
+    path = _small_config(tmp_path, "FP_DM_Oracle", num_runs=2, num_iter=1, rounds_per_iter=200)
+    with pytest.raises(ag.AgymError, match="not built yet"):
+        ag.run_experiment(path)

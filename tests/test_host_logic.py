@@ -1,0 +1,128 @@
+"""CPU: host-side mirror of the reference interface -- config parsing, class table, mechanisms, run sharding,
+CSV schema.  No device work."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import auction_gym_b200 as ag
+from auction_gym_b200 import driver
+from oracle import auction_oracle as ao
+from tests.conftest import ROOT
+
+
+def test_parse_config_reproduces_the_reference_catalog():
+    # known answers: the unmodified reference's parse_config on its own config/SP_Oracle.json, seed 0 (numpy 2.3 PCG64)
+    rng, config, agent_configs, E, V, num_runs, max_slots, D, var, Do = ag.parse_config(os.path.join(ROOT, "config", "SP_Oracle.json"))
+    assert (num_runs, max_slots, D, var, Do) == (3, 1, 5, 1.0, 4)
+    assert [ac["name"] for ac in agent_configs] == [f"Truthful Oracle {k}" for k in range(1, 7)]
+    Es, Vs = np.stack([E[k] for k in E]), np.stack([V[k] for k in V])
+    assert Es.shape == (6, 12, 6) and Vs.shape == (6, 12)
+    assert float(Es.sum()) == pytest.approx(-265.7772298549855, rel=1e-14)
+    assert float(Vs.sum()) == pytest.approx(80.7858057403378, rel=1e-14)
+    assert float(Es[0, 0, 0]) == 0.1257302210933933 and float(Es[5, 11, 5]) == -3.652348965689021 and float(Vs[3, 7]) == 1.6883650018900054
+    _, _, ac, E, V, *_ = ag.parse_config(os.path.join(ROOT, "config", "FP_DR_TS.json"))
+    assert list(E) == ["DR 1", "DR 2", "DR 3"]
+    assert float(np.stack(list(E.values())).sum()) == pytest.approx(-122.00579069546444, rel=1e-14)
+
+
+@pytest.mark.parametrize("cfg", ["SP_Oracle", "SP_Truthful_TS", "FP_DM_Oracle", "FP_DM_TS", "FP_DR_TS", "FP_IPS_TS"])
+def test_every_shipped_config_instantiates(cfg):
+    rng, config, agent_configs, E, V, *_ = ag.parse_config(os.path.join(ROOT, "config", cfg + ".json"))
+    agents = ag.instantiate_agents(rng, agent_configs, V, E)
+    assert len(agents) == len(agent_configs)
+    a0 = agents[0]
+    assert type(a0.allocator).__name__ == agent_configs[0]["allocator"]["type"]
+    assert type(a0.bidder).__name__ == agent_configs[0]["bidder"]["type"]
+    assert a0.bidder.truthful == (agent_configs[0]["bidder"]["type"] == "TruthfulBidder")
+    if cfg == "FP_DM_Oracle":
+        assert a0.bidder.inference == "search" and a0.bidder.kind == ag._lib.BID_SEARCH and a0.bidder.gamma_sigma == 0.02
+        assert a0.allocator.item_embeddings is E[a0.name]
+    if cfg == "FP_IPS_TS":
+        assert a0.bidder.loss == "PPO" and a0.allocator.thompson_sampling and a0.allocator.response_model.m.shape == (12, 5)
+    if cfg == "FP_DM_TS":
+        assert a0.bidder.kind == ag._lib.BID_POLICY
+
+
+def test_kwargs_decoding_and_unknown_types():
+    assert driver.parse_kwargs({"inference": "\"search\"", "gamma_sigma": 0.02, "flag": True}) == {"inference": "search", "gamma_sigma": 0.02, "flag": True}
+    with pytest.raises(ValueError, match="unknown type"):
+        driver.build("NoSuchBidder", None, {})
+    assert ag.LogisticTSAllocator is ag.PyTorchLogisticRegressionAllocator  # stale name in src/main.py:16 / BASELINE.json
+
+
+def test_mechanisms_match_the_oracle_rule():
+    rng = np.random.default_rng(0)
+    for P in (1, 2, 3, 7):
+        bids = rng.random((50, P))
+        bids[::5] = np.round(bids[::5], 1)  # force ties
+        for mech, code in ((ag.FirstPrice(), ao.MECH_FIRST), (ag.SecondPrice(), ao.MECH_SECOND)):
+            assert mech.code == code
+            w, price, second, valid = ao.resolve(bids, code)
+            for t in range(len(bids)):
+                winners, prices, seconds = mech.allocate(bids[t], 1)
+                assert winners[0] == w[t]
+                if P == 1:
+                    assert (len(prices) == 0) if code == ao.MECH_SECOND else (len(seconds) == 0)  # AuctionAllocation.py:22,34
+                else:
+                    assert prices[0] == price[t] and seconds[0] == second[t]
+
+
+def test_shard_runs_is_a_partition():
+    for R in (1, 3, 8, 10, 4096):
+        for world in (1, 2, 3, 8):
+            spans = [ag.shard_runs(R, world, r) for r in range(world)]
+            assert sum(c for _, c in spans) == R
+            nxt = 0
+            for first, count in spans:
+                assert first == nxt and count >= 0
+                nxt += count
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_csv_schema(tmp_path):
+    import pandas as pd
+
+    R, N, A = 2, 3, 3
+    rng = np.random.default_rng(0)
+    cfg = json.load(open(os.path.join(ROOT, "config", "FP_DR_TS.json")))
+    cfg.update(num_runs=R, num_iter=N)
+    names = ["DR 1", "DR 2", "DR 3"]
+    result = {"config": cfg, "agent_names": names, "metrics": rng.random((R, N, A, len(driver.MEASURES))), "revenue": rng.random((R, N)),
+              "truthful": [False] * A}
+    out = driver.write_csvs(result, str(tmp_path))
+    sfx = "10000_rounds_3_iters_2_runs_4_emb_of_5"  # main.py:270 naming
+    files = sorted(os.listdir(out))
+    assert files == sorted(f"{p}_{sfx}.csv" for p in ("net_utility", "gross_utility", "overbid_regret", "underbid_regret", "results"))
+    net = pd.read_csv(f"{out}/net_utility_{sfx}.csv")
+    assert list(net.columns) == ["Run", "Agent", "Iteration", "Net Utility"]
+    assert net[["Agent", "Run", "Iteration"]].values.tolist() == sorted(net[["Agent", "Run", "Iteration"]].values.tolist())  # main.py:270
+    ob = pd.read_csv(f"{out}/overbid_regret_{sfx}.csv")
+    assert list(ob.columns) == ["Run", "Agent", "Iteration", "Overbid Regret"]
+    assert ob["Run"].tolist() == sorted(ob["Run"].tolist())  # unsorted in the reference = run-major insertion order (main.py:228-237)
+    res = pd.read_csv(f"{out}/results_{sfx}.csv")
+    assert list(res.columns) == ["Run", "Iteration", "Measure", "Measure Name"]
+    assert res["Measure Name"].unique().tolist() == ["Auction Revenue", "Social Surplus", "Social Welfare"]
+    surplus = res[res["Measure Name"] == "Social Surplus"].sort_values(["Run", "Iteration"])["Measure"].values
+    np.testing.assert_allclose(surplus, result["metrics"][..., 0].sum(axis=2).ravel())
+
+
+def test_bare_name_modules_like_the_reference():
+    sys.path.insert(0, os.path.join(ROOT, "auction-gym_b200", "src"))
+    try:
+        import importlib
+
+        for mod, names in (("Agent", ["Agent"]), ("Auction", ["Auction"]), ("AuctionAllocation", ["FirstPrice", "SecondPrice"]),
+                           ("Bidder", ["TruthfulBidder", "ValueLearningBidder", "PolicyLearningBidder", "DoublyRobustBidder", "EmpiricalShadedBidder"]),
+                           ("BidderAllocation", ["OracleAllocator", "PyTorchLogisticRegressionAllocator"]),
+                           ("Impression", ["ImpressionOpportunity"]), ("Models", ["sigmoid"]),
+                           ("main", ["parse_config", "instantiate_agents", "instantiate_auction"])):
+            m = importlib.import_module(mod)
+            for n in names:
+                assert hasattr(m, n), (mod, n)
+    finally:
+        sys.path.pop(0)
+        for mod in ("Agent", "Auction", "AuctionAllocation", "Bidder", "BidderAllocation", "Impression", "Models", "main"):
+            sys.modules.pop(mod, None)
