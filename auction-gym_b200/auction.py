@@ -145,11 +145,13 @@ class Auction:
 
     def _agent_logs(self, index):
         cols = self._log_columns()
-        return [] if cols is None else materialise_logs(cols, index, self.D_ctx)
+        if cols is None or index in self._cleared:  # clear_logs() of this agent already ran (Agent.py:124-126)
+            return []
+        return materialise_logs(cols, index, self.D_ctx)
 
     def _agent_log_column(self, index, name):
         cols = self._log_columns()
-        if cols is None:
+        if cols is None or index in self._cleared:
             return []
         return list(cols[name][cols["agent"] == index])
 

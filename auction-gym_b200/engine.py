@@ -218,12 +218,12 @@ class Engine:
         return int(self.lib.agym_rounds_in_iteration(self.handle))
 
     # ------------------------------------------------------------------ updates
-    def update_allocators(self, max_epochs=0, want_info=True):
+    def update_allocators(self, max_epochs=0, want_info=True, fit_mode=0):
         """Agent.update -> allocator.update for every (run, learnt agent) (BidderAllocation.py:29-65)."""
         if not self.any_learnt:
             return None
         info = torch.zeros((self.R, self.A, 4), dtype=torch.float32, device=self.device) if want_info else None
-        self._check(self.lib.agym_update_allocators(self.handle, 0, int(max_epochs), _ptr(info), self._stream()))
+        self._check(self.lib.agym_update_allocators(self.handle, int(fit_mode), int(max_epochs), _ptr(info), self._stream()))
         return info
 
     # ------------------------------------------------------------------ staged kernels

@@ -168,7 +168,10 @@ int agym_set_rounds_in_iteration(agym_handle* h, int64_t n);
 int agym_clear_iteration(agym_handle* h, void* stream);
 
 /* ---- per-iteration model updates ---- */
-enum agym_fit_mode { AGYM_FIT_ADAM_REF = 0 };
+enum agym_fit_mode {
+  AGYM_FIT_ADAM_REF = 0,  /* IEEE divide / sqrt, accurate expf / logf: the operations torch's CPU kernels perform */
+  AGYM_FIT_ADAM_FAST = 1  /* same state machine with MUFU approximations (~2 ulp); sparse regime only, else == REF */
+};
 /* PyTorchLogisticRegressionAllocator.update for every (run, learnt agent) on the winner records of
  * this iteration (BidderAllocation.py:29-65, Models.py:35-48).  fit_info (device, nullable)
  * [R][A][4] float: {stop_epoch or -1, epochs run, final loss, rows}. */

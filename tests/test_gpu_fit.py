@@ -46,7 +46,8 @@ def _stop_close(got, want):
 
 @pytest.mark.parametrize("name", ["fit_ref_shape", "fit_64x64"])
 @pytest.mark.parametrize("it", [0, 1])
-def test_fit_matches_reference_and_oracle(name, it):
+@pytest.mark.parametrize("fit_mode", [0, 1])  # AGYM_FIT_ADAM_REF, AGYM_FIT_ADAM_FAST: same bar for both
+def test_fit_matches_reference_and_oracle(name, it, fit_mode):
     import torch
 
     gu = _gpu()
@@ -72,7 +73,7 @@ def test_fit_matches_reference_and_oracle(name, it):
     eng._check(eng.lib.agym_set_rounds_in_iteration(eng.handle, T))
     eng.set_allocator_state(np.stack([z[p + "m0"] for p in pre])[None], np.stack([z[p + "q0"] for p in pre])[None],
                             np.stack([z[p + "m_prev"] for p in pre])[None])
-    info = eng.update_allocators().cpu().numpy()[0]
+    info = eng.update_allocators(fit_mode=fit_mode).cpu().numpy()[0]
     m1, q1 = eng.m.cpu().numpy()[0], eng.q.cpu().numpy()[0]
     sg = eng.sigma.cpu().numpy()[0]
     mp = eng.m_prev.cpu().numpy()[0]

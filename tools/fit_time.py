@@ -23,7 +23,7 @@ res = []
 for rep in range(REPS):
     eng.set_allocator_state(m0, torch.ones_like(m0))
     torch.cuda.synchronize(); t0 = time.time()
-    info = eng.update_allocators(max_epochs=ME)
+    info = eng.update_allocators(max_epochs=ME, fit_mode=int(__import__('os').environ.get('FIT_MODE','0')))
     torch.cuda.synchronize(); dt = time.time() - t0
     inf = info.cpu().numpy()
     res.append(dt)
