@@ -67,16 +67,16 @@ def test_deterministic_chunked_and_sharded(name):
     full.close()
 
 
-@pytest.mark.parametrize("name", ["rounds_sp_ts", "rounds_fp_gauss", "rounds_sp_oracle_64x64", "rounds_sp_p3", "rounds_fp_ts_gauss"])
-def test_staged_pipeline_equals_fused(name):
+@pytest.mark.parametrize("name,T", [("rounds_sp_ts", 512), ("rounds_fp_gauss", 512), ("rounds_sp_oracle_64x64", 512), ("rounds_sp_p3", 512),
+                                    ("rounds_fp_ts_gauss", 512), ("rounds_fp_gauss", 2052), ("rounds_sp_ts", 1536), ("rounds_sp_oracle_64x64", 4000)])
+def test_staged_pipeline_equals_fused(name, T):
     """K1 -> K2 -> K3 -> K4 through HBM reproduces the fused FP32 kernel exactly (same Philox counters)."""
     gu = _gpu()
     from auction_gym_b200 import _lib
 
     case, *_ = load_golden(name)
-    R, T, seed = 3, 512, 99
+    R, seed = 3, 99  # T >= 1024 takes the CTA-aggregating K4 path (float partial sums per 1024 opportunities)
     eng = gu.engine_from_case(case, R=R, precision=_lib.FP32)
-    P = eng.P
     f = _np(eng.simulate(seed, 1, T, FIELDS + ("value", "best_ev", "second", "gamma")))
     acc_f, rev_f = eng.metrics()
     eng.clear_iteration()
@@ -92,7 +92,7 @@ def test_staged_pipeline_equals_fused(name):
     np.testing.assert_array_equal(sh(s["price"]).astype(np.float64), f["price"][:, :, 0])
     assert np.array_equal(sh(s["outcome"]), f["outcome"].max(axis=2))
     cols = [c for c in range(_lib.NUM_METRICS) if c != _lib.M_BIAS]  # K4's contract carries no estimate
-    np.testing.assert_allclose(acc_s[..., cols], acc_f[..., cols], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(acc_s[..., cols], acc_f[..., cols], rtol=1e-12 if T < 1024 else 5e-6, atol=1e-12 if T < 1024 else 1e-5)
     np.testing.assert_allclose(rev_s, rev_f, rtol=1e-6)
     eng.close()
 
