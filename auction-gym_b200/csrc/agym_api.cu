@@ -114,7 +114,7 @@ int agym_destroy(agym_handle* h) {
   DeviceGuard g(h->device);
   cudaFree(h->d_n_items); cudaFree(h->d_alloc_kind); cudaFree(h->d_bidder_kind);
   cudaFree(h->d_E64); cudaFree(h->d_V64); cudaFree(h->d_E32); cudaFree(h->d_V32);
-  cudaFree(h->d_adam_sz0); cudaFree(h->d_adam_bc2s);
+  cudaFree(h->d_adam_sz0); cudaFree(h->d_adam_bc2s); cudaFree(h->k4_scratch);
   delete h;
   return AGYM_OK;
 }

@@ -184,7 +184,8 @@ struct agym_handle {
   float* d_E32 = nullptr;
   float* d_V32 = nullptr;
   double* d_adam_sz0 = nullptr;  // [kAdamTable] 2e-3 / (1 - 0.9^t), t = epoch + 1 (torch Adam step size at lr 2e-3)
-  float* d_adam_bc2s = nullptr;  // [kAdamTable] sqrt(1 - 0.999^t)
+  float* d_adam_bc2s = nullptr;
+  float* k4_scratch = nullptr;   // [R][A][8 buckets][8] float partial sums of the staged resolution kernel (lazy)  // [kAdamTable] sqrt(1 - 0.999^t)
   bool agents_set = false, catalog_set = false;
   bool any_learnt = false, any_shaded = false;
   int max_items = 0;

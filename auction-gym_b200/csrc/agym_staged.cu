@@ -223,76 +223,86 @@ __global__ void __launch_bounds__(256) k4_kernel_p2(const SimParams p, const flo
 }
 
 // P == 2 with accumulation (K4 + K5): the same resolution, plus charge / set_price bookkeeping (Agent.py:70-77,
-// 104-112, Auction.py:74).  Winner-side sums are first accumulated per CTA in shared memory -- a CTA covers 1024
-// consecutive opportunities, i.e. at most two runs -- and flushed with one FP64 atomic per touched (run, agent,
-// metric): ~16x fewer global atomics than one per opportunity.
-constexpr int kK4Cols = 5;  // net, gross, overbid regret, wins, underbid regret
+// 104-112, Auction.py:74).  The four winner-side sums of one opportunity {net, gross, overbid, wins} go out as ONE
+// 128-bit vector reduction (red.global.add.v4.f32, sm_90+) into a float scratch block [R][A][kK4Buckets][8] that is
+// bucketed by CTA (short float partial sums, less same-address contention); k4_fold_kernel adds the scratch into the
+// FP64 accumulators and clears it.  Shared-memory float atomics (a CAS loop on this architecture) and one FP64 atomic
+// per metric were both measured ~4x slower.
+constexpr int kK4Buckets = 8;
 __global__ void __launch_bounds__(256) k4_kernel_p2_acc(const SimParams p, const float4* __restrict__ bid, const float4* __restrict__ ctr,
                                                         const float4* __restrict__ val, const uint2* __restrict__ parts,
                                                         uint32_t* __restrict__ winner, float4* __restrict__ price,
-                                                        float4* __restrict__ second, uint32_t* __restrict__ outcome, long long N4) {
-  extern __shared__ float sacc[];  // [2][A][kK4Cols] then revenue[2]
-  const int A = p.A, nacc = 2 * A * kK4Cols;
-  for (int i = threadIdx.x; i < nacc + 2; i += blockDim.x) sacc[i] = 0.0f;
-  __syncthreads();
+                                                        float4* __restrict__ second, uint32_t* __restrict__ outcome, long long N4,
+                                                        float* __restrict__ scratch) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int run_base = int(((long long)blockIdx.x * blockDim.x * 4) / p.T);
-  if (q < N4) {
-    const long long n0 = q * 4;
-    const int run = int(n0 / p.T);
-    const long long t0 = n0 - (long long)run * p.T;
-    const PhiloxKey key = make_key(p.seed, uint32_t(p.run_offset + run));
-    const uint4 w = click_block(p.round0 + t0, p.iter, key);
-    const float4 b0 = __ldg(bid + 2 * q), b1 = __ldg(bid + 2 * q + 1);
-    const float4 c0 = __ldg(ctr + 2 * q), c1 = __ldg(ctr + 2 * q + 1);
-    const float4 v0 = __ldg(val + 2 * q), v1 = __ldg(val + 2 * q + 1);
-    const uint2 pa = __ldg(parts + q);
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    const uint32_t uu[4] = {w.x, w.y, w.z, w.w};
-    float pr[4], se[4], rev = 0.0f;
-    uint32_t wpack = 0, opack = 0;
-    const bool first = p.mechanism == AGYM_FIRST_PRICE;
-    float* __restrict__ mine = sacc + (run - run_base) * A * kK4Cols;
+  if (q >= N4) return;
+  const long long n0 = q * 4;
+  const int run = int(n0 / p.T);
+  const long long t0 = n0 - (long long)run * p.T;
+  const PhiloxKey key = make_key(p.seed, uint32_t(p.run_offset + run));
+  const uint4 w = click_block(p.round0 + t0, p.iter, key);
+  const float4 b0 = __ldg(bid + 2 * q), b1 = __ldg(bid + 2 * q + 1);
+  const float4 c0 = __ldg(ctr + 2 * q), c1 = __ldg(ctr + 2 * q + 1);
+  const float4 v0 = __ldg(val + 2 * q), v1 = __ldg(val + 2 * q + 1);
+  const uint2 pa = __ldg(parts + q);
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+  const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  const uint32_t uu[4] = {w.x, w.y, w.z, w.w};
+  float pr[4], se[4], rev = 0.0f;
+  uint32_t wpack = 0, opack = 0;
+  const bool first = p.mechanism == AGYM_FIRST_PRICE;
+  float* __restrict__ mine = scratch + ((size_t)run * p.A * kK4Buckets + (blockIdx.x % kK4Buckets)) * 8;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float x = bb[2 * j], y = bb[2 * j + 1];
-      const int ws = y > x ? 1 : 0;  // lowest slot on ties
-      const float hi = ws ? y : x, lo = ws ? x : y;
-      se[j] = lo;
-      pr[j] = first ? hi : lo;
-      const bool click = u32_to_unit(uu[j]) < cc[2 * j + ws];
-      wpack |= uint32_t(ws) << (8 * j);
-      opack |= uint32_t(click) << (8 * j);
-      const uint32_t pw = (j < 2 ? pa.x : pa.y) >> (16 * (j & 1));
-      const int ag_w = int((pw >> (8 * ws)) & 0xFF), ag_l = int((pw >> (8 * (1 - ws))) & 0xFF);
-      const float got = click ? vv[2 * j + ws] : 0.0f;
-      float* __restrict__ aw = mine + ag_w * kK4Cols;
-      atomicAdd(aw + 0, got - pr[j]);
-      atomicAdd(aw + 1, got);
-      if (first) atomicAdd(aw + 2, pr[j] - lo);
-      atomicAdd(aw + 3, 1.0f);
-      const float tv_l = cc[2 * j + 1 - ws] * vv[2 * j + 1 - ws];
-      if (pr[j] < tv_l) atomicAdd(mine + ag_l * kK4Cols + 4, pr[j] - lo);  // loser's bid is `lo`
-      rev += pr[j];
-    }
-    winner[q] = wpack;
-    outcome[q] = opack;
-    price[q] = make_float4(pr[0], pr[1], pr[2], pr[3]);
-    second[q] = make_float4(se[0], se[1], se[2], se[3]);
-    atomicAdd(sacc + nacc + (run - run_base), rev);
+  for (int j = 0; j < 4; ++j) {
+    const float x = bb[2 * j], y = bb[2 * j + 1];
+    const int ws = y > x ? 1 : 0;  // lowest slot on ties
+    const float hi = ws ? y : x, lo = ws ? x : y;
+    se[j] = lo;
+    pr[j] = first ? hi : lo;
+    const bool click = u32_to_unit(uu[j]) < cc[2 * j + ws];
+    wpack |= uint32_t(ws) << (8 * j);
+    opack |= uint32_t(click) << (8 * j);
+    const uint32_t pw = (j < 2 ? pa.x : pa.y) >> (16 * (j & 1));
+    const int ag_w = int((pw >> (8 * ws)) & 0xFF), ag_l = int((pw >> (8 * (1 - ws))) & 0xFF);
+    const float got = click ? vv[2 * j + ws] : 0.0f;
+    atomicAdd(reinterpret_cast<float4*>(mine + (size_t)ag_w * kK4Buckets * 8), make_float4(got - pr[j], got, pr[j] - lo, 1.0f));
+    const float tv_l = cc[2 * j + 1 - ws] * vv[2 * j + 1 - ws];
+    if (pr[j] < tv_l && pr[j] != lo) atomicAdd(mine + (size_t)ag_l * kK4Buckets * 8 + 4, pr[j] - lo);  // the loser's bid is `lo`
+    rev += pr[j];
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
-    const float v = sacc[i];
-    if (v != 0.0f) {
-      const int rl = i / (A * kK4Cols), a = (i / kK4Cols) % A, c = i % kK4Cols;
-      const int col = c == 0 ? AGYM_M_NET : c == 1 ? AGYM_M_GROSS : c == 2 ? AGYM_M_OVERBID_REGRET : c == 3 ? AGYM_M_NWON : AGYM_M_UNDERBID_REGRET;
-      atomicAdd(p.acc + ((size_t)(run_base + rl) * A + a) * kNumMetrics + col, double(v));
-    }
+  winner[q] = wpack;
+  outcome[q] = opack;
+  price[q] = make_float4(pr[0], pr[1], pr[2], pr[3]);
+  second[q] = make_float4(se[0], se[1], se[2], se[3]);
+  // revenue: one atomic per warp when the warp sits inside one run (Auction.py:74)
+  const unsigned full = __activemask();
+  const int run_lo = __shfl_sync(full, run, __ffs(full) - 1);
+  if (full == 0xffffffffu && __all_sync(full, run == run_lo)) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) rev += __shfl_xor_sync(full, rev, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(p.revenue + run, double(rev));
+  } else {
+    atomicAdd(p.revenue + run, double(rev));
   }
-  if (threadIdx.x < 2 && sacc[nacc + threadIdx.x] != 0.0f) atomicAdd(p.revenue + run_base + threadIdx.x, double(sacc[nacc + threadIdx.x]));
+}
+
+// scratch [R*A][kK4Buckets][8] -> acc [R*A][12] (FP64), scratch cleared; one thread per (run, agent)
+__global__ void __launch_bounds__(256) k4_fold_kernel(float* __restrict__ scratch, double* __restrict__ acc, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s[5] = {0, 0, 0, 0, 0};
+  float4* sc = reinterpret_cast<float4*>(scratch + (size_t)i * kK4Buckets * 8);
+#pragma unroll
+  for (int b = 0; b < kK4Buckets; ++b) {
+    const float4 u = sc[2 * b], v = sc[2 * b + 1];
+    s[0] += u.x; s[1] += u.y; s[2] += u.z; s[3] += u.w; s[4] += v.x;
+    sc[2 * b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sc[2 * b + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  double* a = acc + (size_t)i * kNumMetrics;
+  a[AGYM_M_NET] += s[0]; a[AGYM_M_GROSS] += s[1]; a[AGYM_M_OVERBID_REGRET] += s[2]; a[AGYM_M_NWON] += s[3];
+  a[AGYM_M_UNDERBID_REGRET] += s[4];
 }
 
 // general P: one thread per opportunity, running top-2
@@ -344,11 +354,17 @@ int launch_k4(agym_handle* h, const SimParams& p, const float* bid, const float*
                        ((uintptr_t)second % 16 == 0) && ((uintptr_t)outcome % 4 == 0);
   if (p.P == 2 && p.T % 4 == 0 && p.round0 % 4 == 0 && aligned) {
     const long long N4 = N / 4;
-    if (accumulate && p.T >= 1024) {
-      const size_t smem = (size_t)(2 * p.A * kK4Cols + 2) * sizeof(float);
-      k4_kernel_p2_acc<<<unsigned((N4 + 255) / 256), 256, smem, s>>>(p, (const float4*)bid, (const float4*)true_ctr, (const float4*)value,
-                                                                    (const uint2*)parts, (uint32_t*)winner, (float4*)price,
-                                                                    (float4*)second, (uint32_t*)outcome, N4);
+    if (accumulate) {
+      const size_t nsc = (size_t)p.R * p.A * kK4Buckets * 8;
+      if (h->k4_scratch == nullptr) {  // first use: allocate + clear (configuration-time cost, synchronous)
+        cudaError_t e = cudaMalloc(&h->k4_scratch, nsc * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemset(h->k4_scratch, 0, nsc * sizeof(float));
+        if (e != cudaSuccess) return check_cuda(h, e, "k4 scratch");
+      }
+      k4_kernel_p2_acc<<<unsigned((N4 + 255) / 256), 256, 0, s>>>(p, (const float4*)bid, (const float4*)true_ctr, (const float4*)value,
+                                                                 (const uint2*)parts, (uint32_t*)winner, (float4*)price,
+                                                                 (float4*)second, (uint32_t*)outcome, N4, h->k4_scratch);
+      k4_fold_kernel<<<unsigned((p.R * p.A + 255) / 256), 256, 0, s>>>(h->k4_scratch, p.acc, p.R * p.A);
       return check_cuda(h, cudaGetLastError(), "k4_kernel_p2_acc");
     }
     k4_kernel_p2<<<unsigned((N4 + 255) / 256), 256, 0, s>>>(p, (const float4*)bid, (const float4*)true_ctr, (const float4*)value,
