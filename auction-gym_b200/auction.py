@@ -87,7 +87,10 @@ class Auction:
         if eng.any_shaded:
             pg = np.array([ag.bidder._gamma_params()[0] for ag in self.agents])
             sg = np.array([ag.bidder._gamma_params()[1] for ag in self.agents])
-            eng.set_bidder_state(pg[None, :], sg[None, :])
+            # PyTorchWinRateEstimator = Linear(3, 1): torch's default init is U(-1/sqrt(3), 1/sqrt(3)) for weight and bias
+            # (Models.py:55-58); one independent draw per (run, agent), from the seed instead of torch's global generator
+            wr = np.random.default_rng([self.init_seed, self.run_offset, 0x7772]).uniform(-1, 1, (self.num_runs, A, 4)) / np.sqrt(3.0)
+            eng.set_bidder_state(pg[None, :], sg[None, :], winrate_w=wr)
         self.engine = eng
         self.D_ctx = [D if isinstance(ag.allocator, OracleAllocator) else Do for ag in self.agents]  # Auction.py:46-49
 
@@ -130,11 +133,12 @@ class Auction:
     def _update_models(self):
         if self._models_updated or self.engine is None:
             return
-        unsupported = sorted({type(ag.bidder).__name__ for ag in self.agents if ag.bidder.needs_fit})
+        unsupported = sorted({type(ag.bidder).__name__ for ag in self.agents if ag.bidder.needs_fit and not ag.bidder.fit_built})
         if unsupported:
-            raise _lib.AgymError(f"bidder update for {unsupported} (K7, src/Bidder.py:60-147,210-325,369-431,477-615) is not built yet; "
+            raise _lib.AgymError(f"bidder update for {unsupported} (K7, src/Bidder.py:60-147,278-316,369-431,477-615) is not built yet; "
                                  "see DESIGN.md 'not yet built'")
         self.engine.update_allocators(want_info=False)
+        self.engine.update_bidders(want_info=False)
         self._models_updated = True
 
     # ------------------------------------------------------------------ logs

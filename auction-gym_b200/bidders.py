@@ -13,7 +13,8 @@ class Bidder:
     """Bidder base class (Bidder.py:15-25)."""
 
     kind = _lib.BID_TRUTHFUL
-    needs_fit = False
+    needs_fit = False   # update() does something in the reference
+    fit_built = False   # ... and the engine has that update (agym_update_bidders)
 
     def __init__(self, rng):
         self.rng = rng
@@ -90,7 +91,14 @@ class ValueLearningBidder(_ShadedBidder):
         super().__init__(rng, gamma_sigma, init_gamma)
         self.inference = inference
         self.kind = _lib.BID_SEARCH if inference == "search" else _lib.BID_POLICY
-        self.model_initialised = False
+        self.fit_built = inference == "search"  # the win-rate fit + grid search; the learnt-policy variant is not built yet
+
+    @property
+    def model_initialised(self):  # Bidder.py:168,214,325 -- per run once attached
+        if self._auction is None or self._auction.engine is None:
+            return False
+        v = self._auction.engine.bidder_d[:, self._index, 2].cpu().numpy() != 0
+        return bool(v[0]) if len(v) == 1 else v
 
 
 class PolicyLearningBidder(_ShadedBidder):

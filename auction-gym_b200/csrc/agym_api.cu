@@ -33,6 +33,7 @@ SimParams make_params(const agym_handle* h) {
   p.bidder_d = h->bidder_d; p.bidder_w = h->bidder_w;
   p.acc = h->acc; p.revenue = h->revenue;
   p.fit_ctx = h->fit_ctx; p.fit_meta = h->fit_meta; p.Tcap = h->Tcap;
+  p.bid_rows = h->bid_rows; p.bid_meta = h->bid_meta; p.bid_Tcap = h->bid_Tcap;
   p.round0 = h->rounds_in_iter;
   p.run0 = 0; p.n_runs = s.R;
   return p;
@@ -87,7 +88,9 @@ int agym_create(const agym_shape* shape, int device, agym_handle** out) {
             cudaMalloc(&h->d_V64, nV * sizeof(double)) == cudaSuccess && cudaMalloc(&h->d_E32, nE * sizeof(float)) == cudaSuccess &&
             cudaMalloc(&h->d_V32, nV * sizeof(float)) == cudaSuccess &&
             cudaMalloc(&h->d_adam_sz0, kAdamTable * sizeof(double)) == cudaSuccess &&
-            cudaMalloc(&h->d_adam_bc2s, kAdamTable * sizeof(float)) == cudaSuccess;
+            cudaMalloc(&h->d_adam_bc2s, kAdamTable * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&h->d_adam_bc1, kAdamTable2 * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&h->d_adam_bc2s2, kAdamTable2 * sizeof(float)) == cudaSuccess;
   if (ok) {
     // torch.optim.Adam's per-step scalars, computed the way torch does (Python floats: beta ** step)
     std::vector<double> sz0(kAdamTable);
@@ -97,7 +100,16 @@ int agym_create(const agym_shape* shape, int device, agym_handle** out) {
       sz0[e] = 2e-3 / (1.0 - std::pow(0.9, t));
       bc2s[e] = float(std::sqrt(1.0 - std::pow(0.999, t)));
     }
-    ok = cudaMemcpy(h->d_adam_sz0, sz0.data(), kAdamTable * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+    std::vector<double> bc1(kAdamTable2);
+    std::vector<float> bc2s2(kAdamTable2);
+    for (int e = 0; e < kAdamTable2; ++e) {
+      const double t = double(e + 1);
+      bc1[e] = 1.0 - std::pow(0.9, t);
+      bc2s2[e] = float(std::sqrt(1.0 - std::pow(0.999, t)));
+    }
+    ok = cudaMemcpy(h->d_adam_bc1, bc1.data(), kAdamTable2 * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(h->d_adam_bc2s2, bc2s2.data(), kAdamTable2 * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(h->d_adam_sz0, sz0.data(), kAdamTable * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(h->d_adam_bc2s, bc2s.data(), kAdamTable * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
   }
   if (!ok) {
@@ -114,7 +126,7 @@ int agym_destroy(agym_handle* h) {
   DeviceGuard g(h->device);
   cudaFree(h->d_n_items); cudaFree(h->d_alloc_kind); cudaFree(h->d_bidder_kind);
   cudaFree(h->d_E64); cudaFree(h->d_V64); cudaFree(h->d_E32); cudaFree(h->d_V32);
-  cudaFree(h->d_adam_sz0); cudaFree(h->d_adam_bc2s); cudaFree(h->k4_scratch);
+  cudaFree(h->d_adam_sz0); cudaFree(h->d_adam_bc2s); cudaFree(h->k4_scratch); cudaFree(h->d_adam_bc1); cudaFree(h->d_adam_bc2s2);
   delete h;
   return AGYM_OK;
 }
@@ -123,7 +135,7 @@ int agym_set_agents(agym_handle* h, const int32_t* n_items, const int32_t* alloc
   if (!h || !n_items || !alloc_kind || !bidder_kind) return set_error(h, AGYM_ERR_INVALID, "agym_set_agents: null argument");
   DeviceGuard g(h->device);
   const int A = h->shape.A;
-  h->any_learnt = h->any_shaded = false;
+  h->any_learnt = h->any_shaded = h->any_search = h->any_unbuilt_fit = false;
   h->max_items = 0;
   for (int a = 0; a < A; ++a) {
     if (n_items[a] < 1 || n_items[a] > h->shape.I) return set_error(h, AGYM_ERR_INVALID, "agym_set_agents: n_items out of [1, I]");
@@ -131,6 +143,8 @@ int agym_set_agents(agym_handle* h, const int32_t* n_items, const int32_t* alloc
     if (bidder_kind[a] < AGYM_BID_TRUTHFUL || bidder_kind[a] > AGYM_BID_POLICY) return set_error(h, AGYM_ERR_INVALID, "agym_set_agents: unknown bidder kind");
     h->any_learnt |= alloc_kind[a] != AGYM_ALLOC_ORACLE;
     h->any_shaded |= bidder_kind[a] != AGYM_BID_TRUTHFUL;
+    h->any_search |= bidder_kind[a] == AGYM_BID_SEARCH;
+    h->any_unbuilt_fit |= bidder_kind[a] == AGYM_BID_BANDIT || bidder_kind[a] == AGYM_BID_POLICY;
     if (n_items[a] > h->max_items) h->max_items = n_items[a];
   }
   cudaError_t e = cudaMemcpy(h->d_n_items, n_items, A * sizeof(int), cudaMemcpyHostToDevice);
@@ -189,6 +203,32 @@ int agym_bind_fit_log(agym_handle* h, float* fit_ctx, uint32_t* fit_meta, int64_
   return AGYM_OK;
 }
 
+int agym_bind_bid_log(agym_handle* h, float* bid_rows, uint32_t* bid_meta, int64_t Tcap) {
+  if (!h) return AGYM_ERR_INVALID;
+  if ((bid_rows == nullptr) != (bid_meta == nullptr) || Tcap < 0) return set_error(h, AGYM_ERR_INVALID, "agym_bind_bid_log: bad arguments");
+  h->bid_rows = bid_rows; h->bid_meta = bid_meta; h->bid_Tcap = bid_rows ? Tcap : 0;
+  return AGYM_OK;
+}
+
+size_t agym_bidder_workspace_bytes(const agym_handle* h, int64_t Tcap) { return h ? bidder_workspace_bytes(h, Tcap) : 0; }
+
+int agym_bind_bidder_workspace(agym_handle* h, void* ws, size_t bytes) {
+  if (!h) return AGYM_ERR_INVALID;
+  h->bws = ws; h->bws_bytes = ws ? bytes : 0;
+  return AGYM_OK;
+}
+
+int agym_update_bidders(agym_handle* h, int32_t max_epochs, float* fit_info, void* stream) {
+  if (!h) return AGYM_ERR_INVALID;
+  if (h->any_unbuilt_fit) return set_error(h, AGYM_ERR_UNSUPPORTED, "agym_update_bidders: policy-learning bidder fits (Bidder.py:278-316,369-431,557-615) are not built yet");
+  if (!h->any_search) return AGYM_OK;
+  if (!h->bidder_d || !h->bidder_w) return set_error(h, AGYM_ERR_STATE, "agym_update_bidders: bidder state not bound");
+  if (!h->bid_rows) return set_error(h, AGYM_ERR_STATE, "agym_update_bidders: bid log not bound (agym_bind_bid_log)");
+  if (max_epochs > kAdamTable2) return set_error(h, AGYM_ERR_INVALID, "agym_update_bidders: max_epochs > 32768 (Bidder.py:240)");
+  DeviceGuard g(h->device);
+  return launch_update_bidders(h, max_epochs, fit_info, (cudaStream_t)stream);
+}
+
 size_t agym_workspace_bytes(const agym_handle* h, int64_t Tcap) { return h ? fit_workspace_bytes(h, Tcap) : 0; }
 
 int agym_bind_workspace(agym_handle* h, void* ws, size_t bytes) {
@@ -201,7 +241,7 @@ int64_t agym_rounds_in_iteration(const agym_handle* h) { return h ? h->rounds_in
 
 int agym_set_rounds_in_iteration(agym_handle* h, int64_t n) {
   if (!h) return AGYM_ERR_INVALID;
-  if (n < 0 || (h->fit_ctx && n > h->Tcap)) return set_error(h, AGYM_ERR_INVALID, "agym_set_rounds_in_iteration: out of range");
+  if (n < 0 || (h->fit_ctx && n > h->Tcap) || (h->bid_rows && n > h->bid_Tcap)) return set_error(h, AGYM_ERR_INVALID, "agym_set_rounds_in_iteration: out of range");
   h->rounds_in_iter = n;
   return AGYM_OK;
 }
@@ -219,6 +259,8 @@ int agym_simulate_rounds(agym_handle* h, uint64_t seed, int32_t iter, int64_t T,
   if ((rc = check_bidders_supported(h))) return rc;
   if (h->any_learnt && h->fit_ctx && h->rounds_in_iter + T > h->Tcap)
     return set_error(h, AGYM_ERR_INVALID, "agym_simulate_rounds: fit log capacity exceeded (call agym_clear_iteration or bind a larger log)");
+  if (h->bid_rows && h->rounds_in_iter + T > h->bid_Tcap)
+    return set_error(h, AGYM_ERR_INVALID, "agym_simulate_rounds: bid log capacity exceeded");
   if (T == 0) return AGYM_OK;
   DeviceGuard g(h->device);
   SimParams p = make_params(h);
@@ -235,8 +277,13 @@ int agym_replay_rounds(agym_handle* h, int32_t run0, int32_t n_runs, int64_t T, 
   if (!in->ctx || !in->parts || !in->u) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: ctx, parts and u are required");
   int rc = ready_for_rounds(h, "agym_replay_rounds");
   if (rc) return rc;
-  if (h->any_shaded && !in->gamma_z) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: shaded bidders need gamma_z");
+  if (h->any_shaded && !in->gamma_z && !(h->any_search && in->grid_u && in->grid_n > 0))
+    return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: shaded bidders need gamma_z (and grid_u once a win-rate model is fitted)");
   if (h->fit_ctx && h->rounds_in_iter + T > h->Tcap) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: fit log capacity exceeded");
+  if (h->bid_rows && h->rounds_in_iter + T > h->bid_Tcap) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: bid log capacity exceeded");
+  if (h->any_search && !in->grid_u) {
+    // the 128-point search grid is only needed once some win-rate model is initialised; the kernel reads it lazily
+  }
   if (T == 0) return AGYM_OK;
   DeviceGuard g(h->device);
   SimParams p = make_params(h);

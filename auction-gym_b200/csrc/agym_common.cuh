@@ -11,6 +11,8 @@
 namespace agym {
 
 constexpr int kAdamTable = 16384;  // BidderAllocation.py:38  epochs = 8192 * 2
+constexpr int kAdamTable2 = 32768;  // Bidder.py:240  epochs = 8192 * 4 (win-rate fits)
+constexpr uint32_t kBidValid = 1u << 31, kBidWon = 1u << 30, kBidClick = 1u << 29;
 constexpr int kMaxP = 32;        // participants per round handled by one lane group (P <= group width)
 constexpr int kNumMetrics = AGYM_NUM_METRICS;
 
@@ -50,6 +52,10 @@ struct SimParams {
   float* fit_ctx;      // [R][Tcap][Do]
   uint32_t* fit_meta;  // [R][Tcap]
   long long Tcap;
+  // per-(round, slot) bid records for the bidder fits (optional)
+  float* bid_rows;     // [R][bid_Tcap][P][AGYM_BID_ROW]
+  uint32_t* bid_meta;  // [R][bid_Tcap][P]
+  long long bid_Tcap;
   long long round0;  // rounds already simulated in this iteration (append offset and RNG counter base)
   long long T;       // rounds in this launch
   int run0, n_runs;  // runs covered by this launch
@@ -183,6 +189,8 @@ struct agym_handle {
   double* d_V64 = nullptr;
   float* d_E32 = nullptr;
   float* d_V32 = nullptr;
+  double* d_adam_bc1 = nullptr;  // [kAdamTable2] 1 - 0.9^t
+  float* d_adam_bc2s2 = nullptr; // [kAdamTable2] sqrt(1 - 0.999^t)
   double* d_adam_sz0 = nullptr;  // [kAdamTable] 2e-3 / (1 - 0.9^t), t = epoch + 1 (torch Adam step size at lr 2e-3)
   float* d_adam_bc2s = nullptr;
   float* k4_scratch = nullptr;   // [R][A][8 buckets][8] float partial sums of the staged resolution kernel (lazy)  // [kAdamTable] sqrt(1 - 0.999^t)
@@ -199,6 +207,12 @@ struct agym_handle {
   int64_t Tcap = 0;
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  float* bid_rows = nullptr;
+  uint32_t* bid_meta = nullptr;
+  int64_t bid_Tcap = 0;
+  void* bws = nullptr;
+  size_t bws_bytes = 0;
+  bool any_search = false, any_unbuilt_fit = false;
   int64_t rounds_in_iter = 0;
   int num_sms = 148;
   std::string err;
@@ -214,6 +228,8 @@ int launch_simulate(agym_handle* h, const SimParams& p, const agym_replay_inputs
 int launch_refresh_sigma(agym_handle* h, cudaStream_t s);
 int launch_update_allocators(agym_handle* h, int fit_mode, int max_epochs, float* fit_info, cudaStream_t s);
 size_t fit_workspace_bytes(const agym_handle* h, int64_t Tcap);
+int launch_update_bidders(agym_handle* h, int max_epochs, float* fit_info, cudaStream_t s);
+size_t bidder_workspace_bytes(const agym_handle* h, int64_t Tcap);
 int launch_k1(agym_handle* h, const SimParams& p, float* ctx, uint8_t* parts, cudaStream_t s);
 int launch_k2(agym_handle* h, const SimParams& p, const float* ctx, const uint8_t* parts, uint8_t* item, float* est,
               float* true_ctr, float* best_ev, float* value, cudaStream_t s);

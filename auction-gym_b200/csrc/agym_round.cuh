@@ -185,17 +185,20 @@ __device__ __forceinline__ SlotEval<Real> eval_slot(const SimParams& p, int run,
 }
 
 // Bidder.bid (Bidder.py:34-35,47-58,171-179,348-356,455-463).  gamma / prop stay NaN for truthful bidders.
+// `eff` returns the bid-time behaviour; AGYM_BID_SEARCH is left to search_gamma (it needs the whole lane group).
 template <typename Real>
 __device__ __forceinline__ Real shade_bid(const SimParams& p, int run, int a, int s, Real value, Real est, bool replay,
-                                          double gamma_z_replay, RoundCounter rc, PhiloxKey key, Real& gamma, Real& prop) {
+                                          double gamma_z_replay, RoundCounter rc, PhiloxKey key, Real& gamma, Real& prop,
+                                          int& eff) {
   Real bid = value * est;
   gamma = Real(CUDART_NAN);
   prop = Real(CUDART_NAN);
   const int bkind = p.bidder_kind[a];
+  eff = bkind;
   if (bkind == AGYM_BID_TRUTHFUL) return bid;
   const double* __restrict__ bd = p.bidder_d + ((size_t)run * p.A + a) * AGYM_BIDDER_D;
   const Real prev = Real(bd[0]), sg = Real(bd[1]);
-  const int eff = (bkind >= AGYM_BID_SEARCH && bd[2] == 0.0) ? AGYM_BID_GAUSS : bkind;
+  eff = (bkind >= AGYM_BID_SEARCH && bd[2] == 0.0) ? AGYM_BID_GAUSS : bkind;
   if (eff == AGYM_BID_GAUSS || eff == AGYM_BID_GAUSS_CLIP) {
     Real zg;
     if (replay) zg = Real(gamma_z_replay);
@@ -210,6 +213,53 @@ __device__ __forceinline__ Real shade_bid(const SimParams& p, int run, int a, in
     bid = bid * gamma;
   }
   return bid;
+}
+
+// ValueLearningBidder 'search' (Bidder.py:180-196): 128 gammas ~ U(0.1, 1); P(win | CTR, value, gamma) from the win-rate
+// model (Models.py:61-62, float32 on float32 features); the gamma with the largest estimated utility W * (V - gamma V) is
+// bid.  The reference sorts the grid and takes the first arg-max, i.e. the smallest gamma among equal utilities.
+constexpr int kSearchGrid = 128;
+
+template <typename Real>
+__device__ __forceinline__ void search_point(Real u, Real bid0, float est32, float val32, float w0, float w1, float w2, float b,
+                                             Real& best_u, Real& best_g) {
+  using A_ = Arith<Real>;
+  const Real g = Real(0.1) + (Real(1.0) - Real(0.1)) * u;  // rng.uniform(0.1, 1.0)
+  float z = A_::mac(est32, w0, 0.0f);
+  z = A_::mac(val32, w1, z);
+  z = A_::mac(float(g), w2, z);
+  z = A_::mac(b, 1.0f, z);
+  const Real util = Real(A_::sigmoid32(z)) * (bid0 - bid0 * g);  // Bidder.py:192-194
+  if (util > best_u || (util == best_u && g < best_g)) { best_u = util; best_g = g; }
+}
+
+template <typename Real, int G, bool kReplay>
+__device__ __forceinline__ Real search_gamma(const SimParams& p, int run, int a, int s, Real bid0, Real est, Real value,
+                                             const double* __restrict__ grid_u_slot, int grid_n, RoundCounter rc, PhiloxKey key,
+                                             int lane) {
+  const float* __restrict__ w = p.bidder_w + ((size_t)run * p.A + a) * AGYM_BIDDER_W;
+  const float w0 = w[0], w1 = w[1], w2 = w[2], b = w[3];
+  const float est32 = float(est), val32 = float(value);
+  Real bu = Arith<Real>::neg_inf(), bg = Real(2);
+  if (kReplay) {
+    for (int j = lane; j < grid_n; j += G) search_point<Real>(Real(grid_u_slot[j]), bid0, est32, val32, w0, w1, w2, b, bu, bg);
+  } else {
+    for (int blk = lane; blk < kSearchGrid / 4; blk += G) {
+      const uint4 r = philox4x32_10(rc.c0, rc.c1, (kPurposeGrid << 16) | uint32_t(s), uint32_t(blk), key);
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const Real u = sizeof(Real) == 8 ? Real((double(rr[j]) + 0.5) * (1.0 / 4294967296.0)) : Real(u32_to_unit(rr[j]));
+        search_point<Real>(u, bid0, est32, val32, w0, w1, w2, b, bu, bg);
+      }
+    }
+  }
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) {
+    const Real ou = shfl_xor<G>(bu, off), og = shfl_xor<G>(bg, off);
+    if (ou > bu || (ou == bu && og < bg)) { bu = ou; bg = og; }
+  }
+  return bg;
 }
 
 // Auction.py:65 -- the click uniform of round t is word (t & 3) of Philox block (t >> 2), so the staged

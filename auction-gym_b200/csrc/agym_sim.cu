@@ -62,8 +62,15 @@ __global__ void __launch_bounds__(256) sim_kernel(const SimParams p, const agym_
       const float* eps_slot = (kReplay && in.ts_eps) ? in.ts_eps + ((size_t)ri * P + s) * p.I * p.K : nullptr;
       const SlotEval<Real> ev = eval_slot<Real, G, DMAX, kReplay>(p, run, a, s, ctx, rc, key, eps_slot, lane);
       Real gamma, prop;
-      const Real bid = shade_bid<Real>(p, run, a, s, ev.value, ev.est, kReplay,
-                                       (kReplay && in.gamma_z) ? in.gamma_z[ri * P + s] : 0.0, rc, key, gamma, prop);
+      int eff;
+      Real bid = shade_bid<Real>(p, run, a, s, ev.value, ev.est, kReplay,
+                                 (kReplay && in.gamma_z) ? in.gamma_z[ri * P + s] : 0.0, rc, key, gamma, prop, eff);
+      if (eff == AGYM_BID_SEARCH) {  // Bidder.py:180-196
+        const double* gu = (kReplay && in.grid_u) ? in.grid_u + ((size_t)ri * P + s) * in.grid_n : nullptr;
+        gamma = search_gamma<Real, G, kReplay>(p, run, a, s, bid, ev.est, ev.value, gu, kReplay ? in.grid_n : 0, rc, key, lane);
+        prop = Real(1);
+        bid = bid * gamma;
+      }
       // running top-2, strict '>' keeps the lowest slot on ties (AuctionAllocation.py:19,33)
       if (bid > best) { second = best; best = bid; wslot = s; }
       else if (bid > second) { second = bid; }
@@ -118,6 +125,15 @@ __global__ void __launch_bounds__(256) sim_kernel(const SimParams p, const agym_
         for (int k = 0; k < DMAX; ++k)
           if (k < Do && lane == (k % G)) p.fit_ctx[fi * Do + k] = float(ctx[k]);
         if (lane == 0) p.fit_meta[fi] = valid ? pack_meta(w_agent, w_item, click) : 0u;
+      }
+
+      // ---- bid records for the bidder fits (Agent.py:81-94: bidder.update sees every row) ----
+      if (p.bid_rows != nullptr && ta < p.bid_Tcap && lane < P) {
+        const bool won = valid && lane == wslot;
+        const size_t bi = ((size_t)run * p.bid_Tcap + ta) * P + lane;
+        float* __restrict__ row = p.bid_rows + bi * AGYM_BID_ROW;
+        row[0] = float(r_est); row[1] = float(r_val); row[2] = float(r_gamma); row[3] = float(r_prop); row[4] = float(price);
+        p.bid_meta[bi] = kBidValid | (won ? kBidWon : 0u) | ((won && click) ? kBidClick : 0u) | uint32_t(my_agent);
       }
 
       // ---- detailed log (Impression.py:4-31) ----

@@ -119,7 +119,13 @@ __global__ void __launch_bounds__(256) k3_kernel(const SimParams p, const uint8_
   const RoundCounter rc(p.round0 + t, p.iter);
   const int a = parts[o];
   float g, pr;
-  const float b = shade_bid<float>(p, run, a, s, value[o], est[o], false, 0.0, rc, key, g, pr);
+  int eff;
+  float b = shade_bid<float>(p, run, a, s, value[o], est[o], false, 0.0, rc, key, g, pr, eff);
+  if (eff == AGYM_BID_SEARCH) {  // one thread walks the whole grid here (the fused kernel spreads it over the lane group)
+    g = search_gamma<float, 1, false>(p, run, a, s, b, est[o], value[o], nullptr, 0, rc, key, 0);
+    pr = 1.0f;
+    b *= g;
+  }
   bid[o] = b;
   if (gamma) gamma[o] = g;
   if (prop) prop[o] = pr;

@@ -80,6 +80,8 @@ class Engine:
         self.bidder_w = torch.zeros((self.R, self.A, _lib.BIDDER_W), dtype=torch.float32, device=dev)
         self._check(self.lib.agym_bind_bidder_state(self.handle, _ptr(self.bidder_d), _ptr(self.bidder_w)))
         self.fit_ctx = self.fit_meta = self.workspace = None
+        self.bid_rows = self.bid_meta = self.bidder_workspace = None
+        self.learning_bidders = bool(np.isin(self.bidder_kind, [_lib.BID_SEARCH, _lib.BID_BANDIT, _lib.BID_POLICY]).any())
         self.rounds_capacity = 0
         if rounds_capacity:
             self.reserve_rounds(rounds_capacity)
@@ -109,12 +111,22 @@ class Engine:
         T = int(T)
         if T <= self.rounds_capacity:
             return
-        if not self.any_learnt:
+        if not self.any_learnt and not self.learning_bidders:
             self.rounds_capacity = T
             return
         if int(self.lib.agym_rounds_in_iteration(self.handle)) != 0:
-            raise AgymError("reserve_rounds: cannot grow the winner log in the middle of an iteration")
+            raise AgymError("reserve_rounds: cannot grow the logs in the middle of an iteration")
         dev = self.device
+        if self.learning_bidders:  # per-(round, slot) bid records for the bidder fits
+            self.bid_rows = torch.empty((self.R, T, self.P, _lib.BID_ROW), dtype=torch.float32, device=dev)
+            self.bid_meta = torch.zeros((self.R, T, self.P), dtype=torch.int32, device=dev)
+            self._check(self.lib.agym_bind_bid_log(self.handle, _ptr(self.bid_rows), _ptr(self.bid_meta), T))
+            nb = int(self.lib.agym_bidder_workspace_bytes(self.handle, T))
+            self.bidder_workspace = torch.empty((nb,), dtype=torch.uint8, device=dev)
+            self._check(self.lib.agym_bind_bidder_workspace(self.handle, _ptr(self.bidder_workspace), nb))
+        if not self.any_learnt:
+            self.rounds_capacity = T
+            return
         self.fit_ctx = torch.empty((self.R, T, max(self.Do, 1)), dtype=torch.float32, device=dev)
         self.fit_meta = torch.zeros((self.R, T), dtype=torch.int32, device=dev)
         self._check(self.lib.agym_bind_fit_log(self.handle, _ptr(self.fit_ctx), _ptr(self.fit_meta), T))
@@ -224,6 +236,14 @@ class Engine:
             return None
         info = torch.zeros((self.R, self.A, 4), dtype=torch.float32, device=self.device) if want_info else None
         self._check(self.lib.agym_update_allocators(self.handle, int(fit_mode), int(max_epochs), _ptr(info), self._stream()))
+        return info
+
+    def update_bidders(self, max_epochs=0, want_info=True):
+        """Agent.update -> bidder.update for every (run, agent) whose bidder learns (Bidder.py:210-325)."""
+        if not self.learning_bidders:
+            return None
+        info = torch.zeros((self.R, self.A, 4), dtype=torch.float32, device=self.device) if want_info else None
+        self._check(self.lib.agym_update_bidders(self.handle, int(max_epochs), _ptr(info), self._stream()))
         return info
 
     # ------------------------------------------------------------------ staged kernels

@@ -177,6 +177,22 @@ enum agym_fit_mode {
  * [R][A][4] float: {stop_epoch or -1, epochs run, final loss, rows}. */
 int agym_update_allocators(agym_handle* h, int32_t fit_mode, int32_t max_epochs, float* fit_info, void* stream);
 
+/* Per-(round, slot) bid records that feed the bidder fits (Agent.py:81-94: bidder.update sees ALL rows):
+ * bid_rows [R][Tcap][P][AGYM_BID_ROW] float {estimated CTR, value, gamma, propensity, price},
+ * bid_meta [R][Tcap][P] uint32 (bit 31 valid, bit 30 won, bit 29 click, bits 0..11 agent).
+ * Written by the round loop whenever a log is bound and some agent has a shaded bidder. */
+#define AGYM_BID_ROW 5
+int agym_bind_bid_log(agym_handle* h, float* bid_rows, uint32_t* bid_meta, int64_t Tcap);
+size_t agym_bidder_workspace_bytes(const agym_handle* h, int64_t Tcap);
+int agym_bind_bidder_workspace(agym_handle* h, void* ws, size_t bytes);
+/* Bidder.update for every (run, agent) whose bidder learns (Bidder.py:210-325).  Built so far:
+ * ValueLearningBidder(inference='search'): the win-rate model P(win | CTR, value, gamma) fitted with
+ * Adam(lr 3e-3, weight_decay 1e-6, amsgrad) + ReduceLROnPlateau(patience 100, factor 0.1, min_lr 1e-7) on the logged
+ * rows plus the gamma = 0 augmentation, early stop after 512 epochs without a 1e-6 improvement; sets `initialised`
+ * (or clears it when the agent won nothing, Bidder.py:213-216).  Other learning bidders return AGYM_ERR_UNSUPPORTED.
+ * fit_info (device, nullable) [R][A][4] float: {stop_epoch or -1, epochs run, final loss, rows}. */
+int agym_update_bidders(agym_handle* h, int32_t max_epochs, float* fit_info, void* stream);
+
 /* ---- staged kernels (intermediates in HBM; used for roofline evidence and isolation tests) ---- */
 /* K1  Auction.py:33,42: contexts [N][D] float and participants [N][P] uint8 for N = n_runs*T opportunities */
 int agym_k1_contexts(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, float* ctx, uint8_t* parts, void* stream);

@@ -108,3 +108,66 @@ def fit_allocator(X, items, y, m0, q0, m_prev, max_epochs=MAX_EPOCHS, return_los
     if return_losses:
         out["losses"] = np.asarray(losses)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# ValueLearningBidder / DoublyRobustBidder win-rate model  (Bidder.py:218-260, 501-538; Models.py:51-62)
+# ----------------------------------------------------------------------------------------------
+def fit_winrate(est, value, gamma, won, w0, lr=3e-3, weight_decay=1e-6, patience=100, factor=0.1, min_lr=1e-7,
+                stop_after=512, max_epochs=8192 * 4, return_losses=False):
+    """P(win | est CTR, value, gamma) = sigmoid(w[0:3] . x + w[3]) fitted on the logged rows plus the augmentation
+    "had you shaded to gamma = 0 you would have lost" (Bidder.py:223-236).  Adam(lr, weight_decay, amsgrad=True) +
+    ReduceLROnPlateau(patience, factor, min_lr) + "no 1e-6 improvement for `stop_after` epochs" (Bidder.py:239-260).
+    ValueLearningBidder: patience 100, factor 0.1, stop 512; DoublyRobustBidder: patience 256, factor 0.2, stop 1024.
+    Returns dict(w [4] float32, stop_epoch, n_epochs, final_loss)."""
+    est, value, gamma = (np.asarray(v, f32) for v in (est, value, gamma))
+    n = len(est)
+    X = np.stack([est, value, gamma], axis=1)
+    Xn = X.copy()
+    Xn[:, 2] = 0.0
+    X = np.concatenate([X, Xn]).astype(f32)
+    y = np.concatenate([np.asarray(won, f32), np.zeros(n, f32)])
+    w = np.array(w0, f32, copy=True)
+    N = f32(len(y))
+    ea, es, mx = np.zeros(4, f32), np.zeros(4, f32), np.zeros(4, f32)
+    best_sched, bad = np.inf, 0
+    best_epoch, best_loss = -1, np.inf
+    losses = []
+    stop_epoch = -1
+    for epoch in range(max_epochs):
+        z = (X @ w[:3] + w[3]).astype(f32)
+        p = (f32(1.0) / (f32(1.0) + np.exp(-z))).astype(f32)
+        lp = np.maximum(np.log(p), f32(-100.0))
+        l1p = np.maximum(np.log(f32(1.0) - p), f32(-100.0))
+        loss = f32(-(y * lp + (f32(1.0) - y) * l1p).sum(dtype=f32) / N)  # BCELoss(reduction='mean')
+        g = ((p - y) / N).astype(f32)
+        grad = np.concatenate([X.T @ g, [g.sum(dtype=f32)]]).astype(f32)
+        grad = (grad + f32(weight_decay) * w).astype(f32)  # Adam's L2 weight decay
+        step = epoch + 1
+        ea += (grad - ea) * f32(1 - BETA1)
+        es *= f32(BETA2)
+        es += f32(1 - BETA2) * grad * grad
+        mx = np.maximum(mx, es)  # amsgrad
+        bc1, bc2 = 1 - BETA1 ** step, 1 - BETA2 ** step
+        denom = (np.sqrt(mx) / f32(np.sqrt(bc2)) + f32(ADAM_EPS)).astype(f32)
+        w -= (f32(lr / bc1) * (ea / denom)).astype(f32)
+        cur = float(loss)
+        losses.append(cur)
+        if cur < best_sched * (1.0 - PLATEAU_THRESHOLD):
+            best_sched, bad = cur, 0
+        else:
+            bad += 1
+        if bad > patience:
+            new_lr = max(lr * factor, min_lr)
+            if lr - new_lr > PLATEAU_EPS:
+                lr = new_lr
+            bad = 0
+        if (best_loss - cur) > 1e-6:
+            best_epoch, best_loss = epoch, cur
+        elif epoch - best_epoch > stop_after:
+            stop_epoch = epoch
+            break
+    out = {"w": w, "stop_epoch": stop_epoch, "n_epochs": len(losses), "final_loss": losses[-1]}
+    if return_losses:
+        out["losses"] = np.asarray(losses)
+    return out

@@ -253,3 +253,66 @@ if __name__ == "__main__":
         make_round_goldens()
     if what in ("all", "fit"):
         make_fit_goldens()
+
+
+def make_bidder_goldens():
+    """ValueLearningBidder('search'): the win-rate fit (Bidder.py:210-260) on rows the reference logged, then a second
+    iteration whose bids come from the 128-point grid search (Bidder.py:180-196)."""
+    import torch
+
+    O, GA = ao.ALLOC_ORACLE, ao.BID_GAUSS
+    kw = dict(seed=41, A=6, n_items=12, D=5, Do=4, P=2, mechanism=ao.MECH_FIRST, alloc_kinds=[O] * 6, bidder_kinds=[GA] * 6, T=3000)
+    case, noise, cfg = build_case(**kw)
+    torch.manual_seed(7)  # PyTorchWinRateEstimator init (Models.py:55-58) comes from torch's global generator
+    rec, met, auction, agents = run_reference(case, noise, cfg)
+    out = {}
+    fit_agents = [0, 1, 2, 3, 4, 5]
+    w_after = np.zeros((6, 4), np.float32)
+    for a in fit_agents:
+        ag = agents[a]
+        lin = ag.bidder.winrate_model.model[0]
+        w0 = np.concatenate([lin.weight.detach().numpy().ravel(), lin.bias.detach().numpy()]).astype(np.float32)
+        won = np.array([o.won for o in ag.logs], bool)
+        est = np.array([o.estimated_CTR for o in ag.logs])
+        val = np.array([o.value for o in ag.logs])
+        gam = np.array(ag.bidder.gammas)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            ag.update(iteration=0)
+        mt = re.search(r"Stopping at Epoch (\d+)", buf.getvalue())
+        w1 = np.concatenate([lin.weight.detach().numpy().ravel(), lin.bias.detach().numpy()]).astype(np.float32)
+        w_after[a] = w1
+        pre = f"a{a}_"
+        out[pre + "est"], out[pre + "value"], out[pre + "gamma"], out[pre + "won"] = est, val, gam, won
+        out[pre + "w0"], out[pre + "w1"] = w0, w1
+        out[pre + "stop_epoch"] = int(mt.group(1)) if mt else -1
+        print(f"bidder fit agent {a}: rows {len(won)}, wins {won.sum()}, stop epoch {out[pre + 'stop_epoch']}, w1 {w1}")
+        assert ag.bidder.model_initialised
+    out["fit_agents"] = np.asarray(fit_agents)
+    path = os.path.join(GOLDEN_DIR, "bidfit_winrate.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+    # second iteration: post-fit bids by grid search, replayed
+    for ag in agents:
+        ag.clear_utility()
+        ag.clear_logs()
+    auction.clear_revenue()
+    T2 = 400
+    rng2 = np.random.default_rng(4242)
+    noise2 = ao.draw_replay_inputs(rng2, T2, 6, 2, 5, grid=128)
+    rr = rh.ReplayRNG(noise2["ctx"], noise2["parts"], noise2["u"], None, noise2["grid_u"])
+    auction.rng = rr
+    for ag in agents:
+        ag.bid = type(ag).bid.__get__(ag)
+        ag.bidder.rng = rr
+    rh.wrap_bid_slots(agents, rr)
+    rec2 = rh.run_reference_rounds(auction, agents, rr, T2, None)
+    met2 = rh.reference_metrics(auction, agents)
+    case2 = dict(case)
+    case2["bidder_kind"] = np.full(6, ao.BID_SEARCH, np.int32)
+    case2["winrate_w"] = w_after
+    save_case("rounds_fp_search", case2, noise2, rec2, met2)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "bidder":
+    make_bidder_goldens()

@@ -24,7 +24,10 @@ def engine_from_case(case, R=1, precision=_lib.FP64, run_offset=0, rounds_capaci
         q = np.broadcast_to(case["q"], (R,) + case["q"].shape)
         eng.set_allocator_state(np.ascontiguousarray(m), np.ascontiguousarray(q))
     if eng.any_shaded:
-        eng.set_bidder_state(case["bidder_f"][:, 0][None, :], case["bidder_f"][:, 1][None, :])
+        searching = np.asarray(case["bidder_kind"]) == ao.BID_SEARCH  # fixtures with BID_SEARCH hold a fitted win-rate model
+        eng.set_bidder_state(case["bidder_f"][:, 0][None, :], case["bidder_f"][:, 1][None, :],
+                             initialised=searching[None, :].astype(np.float64),
+                             winrate_w=case["winrate_w"][None] if "winrate_w" in case else None)
     return eng
 
 
@@ -39,4 +42,6 @@ def replay_case(eng, inp, run0=0):
         kw["ts_eps"] = inp["ts_eps"][None]
     if "gamma_z" in inp:
         kw["gamma_z"] = inp["gamma_z"][None]
+    if "grid_u" in inp:
+        kw["grid_u"] = inp["grid_u"][None]
     return eng.replay(inp["ctx"][None], inp["parts"][None], inp["u"][None], run0=run0, **kw)

@@ -1,0 +1,106 @@
+"""GPU parity of the bidder fits (K7) and of post-fit bidding, through the C ABI.
+
+Built so far: ValueLearningBidder(inference='search') -- the win-rate fit (Bidder.py:210-260) and the 128-point grid
+search at bid time (Bidder.py:180-196; replay parity is in test_gpu_rounds.py on tests/golden/rounds_fp_search.npz).
+Tolerance of the fit: like the allocator fit this is an Adam + plateau-scheduler trajectory with an early stop, so the
+bar is |dw| <= 1e-2 on weights of magnitude 1..10, stop epoch +-1 % (+8); against the fit oracle on a fixed epoch budget
+the agreement is ~1e-4.
+"""
+import numpy as np
+import pytest
+
+from oracle import auction_oracle as ao
+from oracle import fit_oracle as fo
+from tests.conftest import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _engine(nA, T, w0, R=1):
+    import torch
+
+    import auction_gym_b200 as ag
+    from auction_gym_b200 import _lib
+
+    E, V = ao.make_catalog(np.random.default_rng(0), nA, 4, 5)
+    eng = ag.Engine(R=R, A=nA, I=4, D=5, Do=4, P=2, mechanism=_lib.FIRST_PRICE, E=E, V=V, n_items=[4] * nA,
+                    alloc_kind=[_lib.ALLOC_ORACLE] * nA, bidder_kind=[_lib.BID_SEARCH] * nA, rounds_capacity=T)
+    eng.set_bidder_state(1.0, 0.02, initialised=0.0, winrate_w=w0)
+    return eng, torch
+
+
+def _fill(eng, torch, run, records):
+    """records: list of (agent, est, value, gamma, won) -> slot 0 of consecutive rounds (slot 1 left invalid)."""
+    n = len(records)
+    rows = np.zeros((n, 2, 5), np.float32)
+    meta = np.zeros((n, 2), np.uint32)
+    for t, (a, e, v, g, won) in enumerate(records):
+        rows[t, 0] = (e, v, g, 1.0, 0.0)
+        meta[t, 0] = (1 << 31) | (int(won) << 30) | int(a)
+    eng.bid_rows[run, :n].copy_(torch.from_numpy(rows))
+    eng.bid_meta[run, :n].copy_(torch.from_numpy(meta.view(np.int32)))
+    return n
+
+
+def test_winrate_fit_matches_reference_and_oracle():
+    _gpu()
+    z = np.load(f"{GOLDEN_DIR}/bidfit_winrate.npz")
+    agents = [int(a) for a in z["fit_agents"]]
+    recs = []
+    per = {a: list(zip(z[f"a{a}_est"], z[f"a{a}_value"], z[f"a{a}_gamma"], z[f"a{a}_won"])) for a in agents}
+    for k in range(max(len(v) for v in per.values())):  # interleave the agents as a real iteration would
+        for j, a in enumerate(agents):
+            if k < len(per[a]):
+                recs.append((j,) + tuple(per[a][k]))
+    w0 = np.stack([z[f"a{a}_w0"] for a in agents])[None]
+    eng, torch = _engine(len(agents), len(recs), w0)
+    n = _fill(eng, torch, 0, recs)
+    eng._check(eng.lib.agym_set_rounds_in_iteration(eng.handle, n))
+    info = eng.update_bidders().cpu().numpy()[0]
+    w1 = eng.bidder_w.cpu().numpy()[0, :, :4]
+    init = eng.bidder_d.cpu().numpy()[0, :, 2]
+    for j, a in enumerate(agents):
+        ref_w, ref_stop = z[f"a{a}_w1"], int(z[f"a{a}_stop_epoch"])
+        what = f"agent {a}: rows {int(info[j, 3])}, stop cuda {int(info[j, 0])} / reference {ref_stop}, w {w1[j]} vs {ref_w}"
+        assert info[j, 3] == len(per[a]) and init[j] == 1.0, what
+        if ref_stop >= 0:
+            assert abs(info[j, 0] - ref_stop) <= max(8, 0.015 * ref_stop), what
+        else:
+            assert info[j, 0] == -1 and info[j, 1] == 32768, what
+        np.testing.assert_allclose(w1[j], ref_w, atol=1e-2, rtol=0, err_msg=what)
+        # what the model is used for: P(win) on a gamma grid (Bidder.py:187-189)
+        g = np.linspace(0.1, 1.0, 64)
+        x = np.stack([np.full(64, 0.12), np.full(64, 1.1), g], axis=1).astype(np.float32)
+        np.testing.assert_allclose(ao.winrate32(w1[j], x), ao.winrate32(ref_w, x), atol=2e-3, err_msg=what)
+    eng.close()
+
+
+def test_winrate_fit_fixed_budget_against_oracle_and_no_win_fallback():
+    _gpu()
+    z = np.load(f"{GOLDEN_DIR}/bidfit_winrate.npz")
+    a = 4
+    rows = list(zip(z[f"a{a}_est"], z[f"a{a}_value"], z[f"a{a}_gamma"], z[f"a{a}_won"]))
+    recs = [(0,) + r for r in rows] + [(1,) + r[:3] + (False,) for r in rows[:50]]  # agent 1 loses every auction
+    w0 = np.stack([z[f"a{a}_w0"], z[f"a{a}_w0"], z[f"a{a}_w0"]])[None]
+    eng, torch = _engine(3, len(recs), w0)
+    eng.bidder_d[0, 1, 2] = 1.0  # agent 1 had a fitted model before
+    n = _fill(eng, torch, 0, recs)
+    eng._check(eng.lib.agym_set_rounds_in_iteration(eng.handle, n))
+    info = eng.update_bidders(max_epochs=600).cpu().numpy()[0]
+    orc = fo.fit_winrate(z[f"a{a}_est"], z[f"a{a}_value"], z[f"a{a}_gamma"], z[f"a{a}_won"], z[f"a{a}_w0"], max_epochs=600)
+    w1 = eng.bidder_w.cpu().numpy()[0, :, :4]
+    init = eng.bidder_d.cpu().numpy()[0, :, 2]
+    assert info[0, 1] == orc["n_epochs"] == 600
+    np.testing.assert_allclose(w1[0], orc["w"], atol=2e-4)
+    np.testing.assert_allclose(info[0, 2], orc["final_loss"], rtol=1e-5)
+    assert init.tolist() == [1.0, 0.0, 0.0]                      # Bidder.py:213-216 fallback for the agent that won nothing
+    assert np.array_equal(w1[1], z[f"a{a}_w0"]) and info[1, 3] == 50 and info[1, 1] == 0
+    assert np.array_equal(w1[2], z[f"a{a}_w0"]) and info[2, 3] == 0  # an agent that never participated: untouched
+    eng.close()

@@ -36,7 +36,7 @@ def test_replay_fp64_matches_oracle_and_reference(name):
     out = gu.replay_case(eng, inp)
     got = gu.log_to_numpy(out)
     assert np.array_equal(got["agent"], inp["parts"])
-    rec, m = ao.simulate_rounds(case, inp["ctx"], inp["parts"], inp["u"], inp.get("ts_eps"), inp.get("gamma_z"))
+    rec, m = ao.simulate_rounds(case, inp["ctx"], inp["parts"], inp["u"], inp.get("ts_eps"), inp.get("gamma_z"), inp.get("grid_u"))
     learnt = bool((case["alloc_kind"] != ao.ALLOC_ORACLE).any())
     est_rtol = parity.RTOL_F32_EST if learnt else parity.RTOL_F64
     # CUDA vs oracle
@@ -60,7 +60,7 @@ def test_replay_fp32_within_tolerance(name):
     case, inp, ref, met = load_golden(name)
     eng = gu.engine_from_case(case, R=1, precision=_lib.FP32)
     got = gu.log_to_numpy(gu.replay_case(eng, inp))
-    rec, m = ao.simulate_rounds(case, inp["ctx"], inp["parts"], inp["u"], inp.get("ts_eps"), inp.get("gamma_z"))
+    rec, m = ao.simulate_rounds(case, inp["ctx"], inp["parts"], inp["u"], inp.get("ts_eps"), inp.get("gamma_z"), inp.get("grid_u"))
     T = inp["parts"].shape[0]
     # float32 decisions: an arg-max may flip only where the float64 margin is below float32 resolution,
     # a click only where u is within float32 resolution of the CTR

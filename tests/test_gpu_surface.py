@@ -115,6 +115,24 @@ def test_unbuilt_bidder_fits_fail_loudly(tmp_path):
     _need_gpu()
     import auction_gym_b200 as ag
 
-    path = _small_config(tmp_path, "FP_DM_Oracle", num_runs=2, num_iter=1, rounds_per_iter=200)
+    path = _small_config(tmp_path, "FP_DR_TS", num_runs=2, num_iter=1, rounds_per_iter=200)
     with pytest.raises(ag.AgymError, match="not built yet"):
         ag.run_experiment(path)
+
+
+def test_first_price_value_learning_config_learns_to_shade(tmp_path):
+    """config/FP_DM_Oracle.json (BASELINE.json configs[2]): after the first win-rate fit the bidders search the gamma grid
+    and shade their bids; first-price revenue drops and bidder surplus rises, as in the reference's figures."""
+    _need_gpu()
+    import auction_gym_b200 as ag
+
+    path = _small_config(tmp_path, "FP_DM_Oracle", num_runs=8, num_iter=3, rounds_per_iter=3000)
+    result = ag.run_experiment(path)
+    m = result["metrics"]  # [R, N, A, 10]
+    gamma = m[..., 9].mean(axis=(0, 2))
+    surplus = m[..., 0].sum(axis=2).mean(axis=0)
+    revenue = result["revenue"].mean(axis=0)
+    assert abs(gamma[0] - 1.0) < 0.01, gamma            # iteration 0: gamma ~ N(1, 0.02)  (Bidder.py:177)
+    assert gamma[1] < 0.97 and gamma[2] < 0.97, gamma   # afterwards: searched gammas in [0.1, 1]
+    assert surplus[1] > surplus[0] and revenue[1] < revenue[0], (surplus, revenue)
+    assert np.isfinite(m).all()

@@ -11,7 +11,7 @@ from tests.conftest import load_golden, round_golden_names
 @pytest.mark.parametrize("name", round_golden_names())
 def test_round_loop_matches_reference(name):
     case, inp, ref, met = load_golden(name)
-    rec, m = ao.simulate_rounds(case, inp["ctx"], inp["parts"], inp["u"], inp.get("ts_eps"), inp.get("gamma_z"))
+    rec, m = ao.simulate_rounds(case, inp["ctx"], inp["parts"], inp["u"], inp.get("ts_eps"), inp.get("gamma_z"), inp.get("grid_u"))
     ref = dict(ref)
     ref["winner"] = np.where(ref["won"].any(axis=1), ref["won"].argmax(axis=1), rec["winner"])
     learnt = bool((case["alloc_kind"] != ao.ALLOC_ORACLE).any())
@@ -26,8 +26,8 @@ def test_scalar_port_equals_vectorised(name):
     case, inp, ref, met = load_golden(name)
     T = min(200, inp["parts"].shape[0])
     sl = {k: v[:T] for k, v in inp.items()}
-    rec_v, m_v = ao.simulate_rounds(case, sl["ctx"], sl["parts"], sl["u"], sl.get("ts_eps"), sl.get("gamma_z"))
-    rec_s, m_s = ao.simulate_rounds_scalar(case, sl["ctx"], sl["parts"], sl["u"], sl.get("ts_eps"), sl.get("gamma_z"))
+    rec_v, m_v = ao.simulate_rounds(case, sl["ctx"], sl["parts"], sl["u"], sl.get("ts_eps"), sl.get("gamma_z"), sl.get("grid_u"))
+    rec_s, m_s = ao.simulate_rounds_scalar(case, sl["ctx"], sl["parts"], sl["u"], sl.get("ts_eps"), sl.get("gamma_z"), sl.get("grid_u"))
     assert np.array_equal(rec_s["winner"], rec_v["winner"])
     assert np.array_equal(rec_s["item"], rec_v["item"])
     assert np.array_equal(rec_s["outcome"], rec_v["outcome"].max(axis=1))
