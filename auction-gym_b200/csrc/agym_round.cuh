@@ -91,12 +91,13 @@ struct SlotEval {
 
 // Agent.select_item + the true-CTR bookkeeping of Auction.py:52-53 for the agent in slot s.
 // Lanes of the group stride over the agent's items; the result is uniform across the group.
-template <typename Real, int G, int DMAX, bool kReplay>
+// DT / DoT > 0 fix embedding_size / obs_embedding_size at compile time (the shipped configs' 5 / 4), 0 = run time.
+template <typename Real, int G, int DMAX, bool kReplay, int DT = 0, int DoT = 0>
 __device__ __forceinline__ SlotEval<Real> eval_slot(const SimParams& p, int run, int a, int s, const Real (&ctx)[DMAX],
                                                     RoundCounter rc, PhiloxKey key, const float* __restrict__ ts_eps_slot,
                                                     int lane) {
   using A_ = Arith<Real>;
-  const int D = p.D, Do = p.Do, K = p.K, I = p.I;
+  const int D = DT > 0 ? DT : p.D, Do = DT > 0 ? DoT : p.Do, K = Do + 1, I = p.I;
   const int nI = p.n_items[a];
   const int akind = p.alloc_kind[a];
   const Real* __restrict__ Ea = Catalog<Real>::E(p) + (size_t)a * I * (D + 1);
