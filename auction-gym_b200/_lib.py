@@ -15,6 +15,7 @@ BIDDER_D = 4
 BIDDER_W = 16
 BID_ROW = 5
 FIT_ADAM_REF, FIT_ADAM_FAST = 0, 1
+(BFIT_NONE, BFIT_VL_SEARCH, BFIT_VL_POLICY, BFIT_PL_REINFORCE, BFIT_PL_OFFPOLICY, BFIT_PL_TRPO, BFIT_PL_PPO, BFIT_DR) = range(8)
 ABI_VERSION = 1
 
 # enum mirrors (include/agym.h)
@@ -74,7 +75,8 @@ SIGNATURES = {
     "agym_bind_bid_log": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64]),
     "agym_bidder_workspace_bytes": (C.c_size_t, [_H, C.c_int64]),
     "agym_bind_bidder_workspace": (C.c_int, [_H, C.c_void_p, C.c_size_t]),
-    "agym_update_bidders": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p]),
+    "agym_set_bidder_fits": (C.c_int, [_H, C.c_void_p]),
+    "agym_update_bidders": (C.c_int, [_H, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "agym_k1_contexts": (C.c_int, [_H, C.c_uint64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "agym_k2_allocate": (C.c_int, [_H, C.c_uint64, C.c_int32, C.c_int64] + [C.c_void_p] * 8),
     "agym_k3_bids": (C.c_int, [_H, C.c_uint64, C.c_int32, C.c_int64] + [C.c_void_p] * 7),

@@ -70,7 +70,8 @@ class Auction:
                      mechanism=self.allocation.code, E=E, V=V, n_items=n_items,
                      alloc_kind=[ag.allocator.kind for ag in self.agents], bidder_kind=[ag.bidder.kind for ag in self.agents],
                      embedding_var=float(self.embedding_var), precision=self.precision, device=self.device,
-                     run_offset=self.run_offset, rounds_capacity=self._rounds_capacity)
+                     run_offset=self.run_offset, rounds_capacity=self._rounds_capacity,
+                     bidder_fit=[ag.bidder.fit_kind for ag in self.agents])
         if eng.any_learnt:
             m = np.zeros((self.num_runs, A, I, Do + 1), np.float32)
             q = np.ones_like(m)
@@ -90,7 +91,9 @@ class Auction:
             # PyTorchWinRateEstimator = Linear(3, 1): torch's default init is U(-1/sqrt(3), 1/sqrt(3)) for weight and bias
             # (Models.py:55-58); one independent draw per (run, agent), from the seed instead of torch's global generator
             wr = np.random.default_rng([self.init_seed, self.run_offset, 0x7772]).uniform(-1, 1, (self.num_runs, A, 4)) / np.sqrt(3.0)
-            eng.set_bidder_state(pg[None, :], sg[None, :], winrate_w=wr)
+            # policy nets (Models.py:71-77,97-101): Linear layers with fan-in 2 -> U(-1/sqrt(2), 1/sqrt(2))
+            pw = np.random.default_rng([self.init_seed, self.run_offset, 0x706f]).uniform(-1, 1, (self.num_runs, A, 12)) / np.sqrt(2.0)
+            eng.set_bidder_state(pg[None, :], sg[None, :], winrate_w=wr, policy_w=pw)
         self.engine = eng
         self.D_ctx = [D if isinstance(ag.allocator, OracleAllocator) else Do for ag in self.agents]  # Auction.py:46-49
 
@@ -138,7 +141,9 @@ class Auction:
             raise _lib.AgymError(f"bidder update for {unsupported} (K7, src/Bidder.py:60-147,278-316,369-431,477-615) is not built yet; "
                                  "see DESIGN.md 'not yet built'")
         self.engine.update_allocators(want_info=False)
-        self.engine.update_bidders(want_info=False)
+        info = self.engine.update_bidders(self.seed, self.iteration)
+        if info is not None and bool((info[..., 1] > 0).logical_and(info[..., 2].isnan()).any()):
+            raise _lib.AgymError("NaN loss in a bidder fit (the reference prints 'NAN DETECTED!' and exits, Bidder.py:412-419,598-605)")
         self._models_updated = True
 
     # ------------------------------------------------------------------ logs

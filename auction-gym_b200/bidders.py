@@ -15,6 +15,7 @@ class Bidder:
     kind = _lib.BID_TRUTHFUL
     needs_fit = False   # update() does something in the reference
     fit_built = False   # ... and the engine has that update (agym_update_bidders)
+    fit_kind = _lib.BFIT_NONE
 
     def __init__(self, rng):
         self.rng = rng
@@ -72,6 +73,13 @@ class _ShadedBidder(Bidder):
     def _gamma_params(self):
         return self.prev_gamma, self.gamma_sigma
 
+    @property
+    def model_initialised(self):  # Bidder.py:168,345,452 -- per run once attached
+        if self._auction is None or self._auction.engine is None:
+            return False
+        v = self._auction.engine.bidder_d[:, self._index, 2].cpu().numpy() != 0
+        return bool(v[0]) if len(v) == 1 else v
+
 
 class EmpiricalShadedBidder(_ShadedBidder):
     """One global gamma ~ N(prev_gamma, sigma) clipped to [0, 1] (Bidder.py:38-58).  Its bucketised
@@ -91,14 +99,9 @@ class ValueLearningBidder(_ShadedBidder):
         super().__init__(rng, gamma_sigma, init_gamma)
         self.inference = inference
         self.kind = _lib.BID_SEARCH if inference == "search" else _lib.BID_POLICY
-        self.fit_built = inference == "search"  # the win-rate fit + grid search; the learnt-policy variant is not built yet
+        self.fit_built = True
+        self.fit_kind = _lib.BFIT_VL_SEARCH if inference == "search" else _lib.BFIT_VL_POLICY
 
-    @property
-    def model_initialised(self):  # Bidder.py:168,214,325 -- per run once attached
-        if self._auction is None or self._auction.engine is None:
-            return False
-        v = self._auction.engine.bidder_d[:, self._index, 2].cpu().numpy() != 0
-        return bool(v[0]) if len(v) == 1 else v
 
 
 class PolicyLearningBidder(_ShadedBidder):
@@ -107,10 +110,16 @@ class PolicyLearningBidder(_ShadedBidder):
     kind = _lib.BID_BANDIT
     needs_fit = True
 
+    fit_built = True
+    _LOSSES = {"REINFORCE": _lib.BFIT_PL_REINFORCE, "REINFORCE_offpolicy": _lib.BFIT_PL_OFFPOLICY, "TRPO": _lib.BFIT_PL_TRPO,
+               "PPO": _lib.BFIT_PL_PPO}
+
     def __init__(self, rng, gamma_sigma, loss, init_gamma=1.0):
         super().__init__(rng, gamma_sigma, init_gamma)
+        if loss not in self._LOSSES:
+            raise ValueError(f"unknown PolicyLearningBidder loss {loss!r} (Models.py:173-196: {sorted(self._LOSSES)})")
         self.loss = loss
-        self.model_initialised = False
+        self.fit_kind = self._LOSSES[loss]
 
 
 class DoublyRobustBidder(_ShadedBidder):
@@ -119,9 +128,11 @@ class DoublyRobustBidder(_ShadedBidder):
     kind = _lib.BID_BANDIT
     needs_fit = True
 
+    fit_built = True
+    fit_kind = _lib.BFIT_DR
+
     def __init__(self, rng, gamma_sigma, init_gamma=1.0):
         super().__init__(rng, gamma_sigma, init_gamma)
-        self.model_initialised = False
 
 
 def gaussian_propensity(prev_gamma, sigma, gamma):

@@ -84,7 +84,7 @@ int agym_create(const agym_shape* shape, int device, agym_handle** out) {
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
   const size_t nE = (size_t)s.A * s.I * (s.D + 1), nV = (size_t)s.A * s.I;
   bool ok = cudaMalloc(&h->d_n_items, s.A * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_alloc_kind, s.A * sizeof(int)) == cudaSuccess &&
-            cudaMalloc(&h->d_bidder_kind, s.A * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_E64, nE * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&h->d_bidder_kind, s.A * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_bidder_fit, s.A * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_E64, nE * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->d_V64, nV * sizeof(double)) == cudaSuccess && cudaMalloc(&h->d_E32, nE * sizeof(float)) == cudaSuccess &&
             cudaMalloc(&h->d_V32, nV * sizeof(float)) == cudaSuccess &&
             cudaMalloc(&h->d_adam_sz0, kAdamTable * sizeof(double)) == cudaSuccess &&
@@ -124,7 +124,7 @@ int agym_create(const agym_shape* shape, int device, agym_handle** out) {
 int agym_destroy(agym_handle* h) {
   if (!h) return AGYM_OK;
   DeviceGuard g(h->device);
-  cudaFree(h->d_n_items); cudaFree(h->d_alloc_kind); cudaFree(h->d_bidder_kind);
+  cudaFree(h->d_n_items); cudaFree(h->d_alloc_kind); cudaFree(h->d_bidder_kind); cudaFree(h->d_bidder_fit);
   cudaFree(h->d_E64); cudaFree(h->d_V64); cudaFree(h->d_E32); cudaFree(h->d_V32);
   cudaFree(h->d_adam_sz0); cudaFree(h->d_adam_bc2s); cudaFree(h->k4_scratch); cudaFree(h->d_adam_bc1); cudaFree(h->d_adam_bc2s2);
   delete h;
@@ -152,7 +152,33 @@ int agym_set_agents(agym_handle* h, const int32_t* n_items, const int32_t* alloc
   if (e == cudaSuccess) e = cudaMemcpy(h->d_bidder_kind, bidder_kind, A * sizeof(int), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return check_cuda(h, e, "agym_set_agents");
   h->agents_set = true;
-  return AGYM_OK;
+  std::vector<int32_t> fits(A);
+  for (int a = 0; a < A; ++a)
+    fits[a] = bidder_kind[a] == AGYM_BID_SEARCH ? AGYM_BFIT_VL_SEARCH : bidder_kind[a] == AGYM_BID_POLICY ? AGYM_BFIT_VL_POLICY : AGYM_BFIT_NONE;
+  return agym_set_bidder_fits(h, fits.data());
+}
+
+int agym_set_bidder_fits(agym_handle* h, const int32_t* fit_kind) {
+  if (!h || !fit_kind) return set_error(h, AGYM_ERR_INVALID, "agym_set_bidder_fits: null argument");
+  if (!h->agents_set) return set_error(h, AGYM_ERR_STATE, "agym_set_bidder_fits: call agym_set_agents first");
+  DeviceGuard g(h->device);
+  const int A = h->shape.A;
+  std::vector<int32_t> kinds(A);
+  cudaError_t e = cudaMemcpy(kinds.data(), h->d_bidder_kind, A * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return check_cuda(h, e, "agym_set_bidder_fits");
+  h->any_winrate_fit = h->any_policy_fit = h->any_unassigned_bandit = false;
+  for (int a = 0; a < A; ++a) {
+    const int f = fit_kind[a], k = kinds[a];
+    if (f < AGYM_BFIT_NONE || f > AGYM_BFIT_DR) return set_error(h, AGYM_ERR_INVALID, "agym_set_bidder_fits: unknown fit kind");
+    const bool ok = (f == AGYM_BFIT_NONE) || (f == AGYM_BFIT_VL_SEARCH && k == AGYM_BID_SEARCH) || (f == AGYM_BFIT_VL_POLICY && k == AGYM_BID_POLICY) ||
+                    (f >= AGYM_BFIT_PL_REINFORCE && k == AGYM_BID_BANDIT);
+    if (!ok) return set_error(h, AGYM_ERR_INVALID, "agym_set_bidder_fits: fit kind does not match the agent's bid kind");
+    h->any_winrate_fit |= f == AGYM_BFIT_VL_SEARCH || f == AGYM_BFIT_VL_POLICY || f == AGYM_BFIT_DR;
+    h->any_policy_fit |= f >= AGYM_BFIT_VL_POLICY;
+    h->any_unassigned_bandit |= (k == AGYM_BID_BANDIT || k == AGYM_BID_POLICY || k == AGYM_BID_SEARCH) && f == AGYM_BFIT_NONE;
+  }
+  e = cudaMemcpy(h->d_bidder_fit, fit_kind, A * sizeof(int), cudaMemcpyHostToDevice);
+  return check_cuda(h, e, "agym_set_bidder_fits");
 }
 
 int agym_set_catalog(agym_handle* h, const double* E, const double* V) {
@@ -218,15 +244,16 @@ int agym_bind_bidder_workspace(agym_handle* h, void* ws, size_t bytes) {
   return AGYM_OK;
 }
 
-int agym_update_bidders(agym_handle* h, int32_t max_epochs, float* fit_info, void* stream) {
+int agym_update_bidders(agym_handle* h, uint64_t seed, int32_t iter, int32_t max_epochs, float* fit_info, void* stream) {
   if (!h) return AGYM_ERR_INVALID;
-  if (h->any_unbuilt_fit) return set_error(h, AGYM_ERR_UNSUPPORTED, "agym_update_bidders: policy-learning bidder fits (Bidder.py:278-316,369-431,557-615) are not built yet");
-  if (!h->any_search) return AGYM_OK;
+  if (h->any_unassigned_bandit)
+    return set_error(h, AGYM_ERR_STATE, "agym_update_bidders: an agent bids with a learnt model but has no fit kind (agym_set_bidder_fits)");
+  if (!h->any_winrate_fit && !h->any_policy_fit) return AGYM_OK;
   if (!h->bidder_d || !h->bidder_w) return set_error(h, AGYM_ERR_STATE, "agym_update_bidders: bidder state not bound");
   if (!h->bid_rows) return set_error(h, AGYM_ERR_STATE, "agym_update_bidders: bid log not bound (agym_bind_bid_log)");
-  if (max_epochs > kAdamTable2) return set_error(h, AGYM_ERR_INVALID, "agym_update_bidders: max_epochs > 32768 (Bidder.py:240)");
+  if (max_epochs < 0) return set_error(h, AGYM_ERR_INVALID, "agym_update_bidders: max_epochs < 0");
   DeviceGuard g(h->device);
-  return launch_update_bidders(h, max_epochs, fit_info, (cudaStream_t)stream);
+  return launch_update_bidders(h, seed, iter, max_epochs, fit_info, (cudaStream_t)stream);
 }
 
 size_t agym_workspace_bytes(const agym_handle* h, int64_t Tcap) { return h ? fit_workspace_bytes(h, Tcap) : 0; }

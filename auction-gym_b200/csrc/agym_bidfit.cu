@@ -1,39 +1,53 @@
-// K7 (first part): ValueLearningBidder.update -- the win-rate model P(win | estimated CTR, value, gamma)
-// (reference src/Bidder.py:210-260, src/Models.py:51-62): logistic regression with 3 weights + bias on the agent's logged
-// rows plus the augmentation "with gamma = 0 you would have lost" (Bidder.py:223-236), BCELoss(mean),
-// Adam(lr 3e-3, weight_decay 1e-6, amsgrad=True), ReduceLROnPlateau(patience 100, factor 0.1, min_lr 1e-7), at most
-// 32 768 epochs, early stop after 512 epochs without a 1e-6 improvement.  An agent that won nothing this iteration gets
-// `initialised = 0` instead (Bidder.py:213-216).
+// K7: the bidder fits of Agent.update -> bidder.update (reference src/Bidder.py:210-325, 369-431, 477-615 and
+// src/Models.py:51-218), one CTA per (run, agent), all epochs on-chip.
 //
-//   bidrows_bucket_kernel  one CTA per run: stable counting sort of the (round, slot) bid records by agent
-//   winrate_fit_kernel     one CTA per (run, agent): rows staged in shared memory as float4 {est, value, gamma, won};
-//                          every epoch is one row-parallel pass (both the logged and the augmented row of a record are
-//                          evaluated together), a 5-value block reduction (loss + 4 gradient components), and the
-//                          4-parameter Adam / scheduler / stop state machine replicated in every thread.
+//   ValueLearningBidder('search')   win-rate fit                                              Bidder.py:210-260
+//   ValueLearningBidder('policy')   win-rate fit, then the policy maximises W * (V - gamma V)  Bidder.py:278-316
+//   PolicyLearningBidder(loss)      [initialise_policy], then REINFORCE / off-policy / TRPO / PPO  Bidder.py:369-431
+//   DoublyRobustBidder              win-rate fit, u_hat = W (V - P), [initialise_policy], DR loss   Bidder.py:477-615
+//
+// Kernels (launched in this order by launch_update_bidders; agents that do not need a stage exit at once):
+//   bidrows_bucket_kernel  CTA per run: stable counting sort of the (round, slot) bid records by agent
+//   gather_rows_kernel     CTA per (run, agent): compact rows {est, value, gamma, propensity | utility, won, u_hat, -}
+//   winrate_fit_kernel     logistic regression (3 weights + bias) with the gamma = 0 augmentation; BCELoss(mean);
+//                          Adam(lr 3e-3, wd 1e-6, amsgrad) + ReduceLROnPlateau + "no 1e-6 improvement" stop
+//   policy_fit_kernel      the 12-parameter Gaussian policy (2 -> 2 -> {mu, sigma}, softplus) with hand-written
+//                          back-propagation; stage IMITATE = initialise_policy (Models.py:110-133), stage MAIN = the
+//                          bidder's loss.  Every epoch: one row-parallel pass, a 13-value block reduction (loss + 12
+//                          gradient components), Adam(amsgrad, weight decay) + scheduler + stop rule replicated per thread.
+// The stochastic objectives (Doubly Robust, 'policy') draw their rsample noise from Philox keyed by
+// (seed, run, iteration, epoch, row), so a fit is reproducible and independent of the launch geometry.
 #include <math_constants.h>
 
 #include "agym_common.cuh"
 
 namespace agym {
 
+constexpr int kRowF = 8;  // floats per compact row
 struct BidFitParams {
   int R, A, P;
   long long Tcap, Tn;
-  const int* bidder_kind;
+  const int* fit_kind;      // [A] agym_bidder_fit
   const float* rows;        // [R][Tcap][P][AGYM_BID_ROW]
   const uint32_t* meta;     // [R][Tcap][P]
   uint32_t* srt_idx;        // [R][Tcap*P] record indices grouped by agent (stable)
   int* aoff;                // [R][A+1]
-  float4* spill;            // [R][Tcap*P] rows that overflow shared memory
+  int* wins;                // [R][A] won rows; -1 = skip the remaining stages (Bidder.py:213-216 fallback)
+  float* crow;              // [R][Tcap*P][kRowF] compact rows, grouped by agent
   double* bidder_d;         // [R][A][AGYM_BIDDER_D]
   float* bidder_w;          // [R][A][AGYM_BIDDER_W]
-  float* info;              // [R][A][4] or null
-  const double* bc1;        // [kAdamTable2]
-  const float* bc2s;        // [kAdamTable2]
-  int max_epochs, ncap;
+  float* info;              // [R][A][4] or null (last stage that ran for the agent)
+  const double* bc1;        // [kAdamTable2]  1 - 0.9^t
+  const float* bc2s;        // [kAdamTable2]  sqrt(1 - 0.999^t)
+  int max_epochs, ncap, stage;
+  int run_offset;
+  uint64_t seed;
+  int iter;
 };
 
-__device__ __forceinline__ bool learns_winrate(int kind) { return kind == AGYM_BID_SEARCH; }
+__device__ __forceinline__ bool fits_winrate(int k) { return k == AGYM_BFIT_VL_SEARCH || k == AGYM_BFIT_VL_POLICY || k == AGYM_BFIT_DR; }
+__device__ __forceinline__ bool fits_policy(int k) { return k >= AGYM_BFIT_VL_POLICY; }
+__device__ __forceinline__ bool needs_imitation(int k) { return k >= AGYM_BFIT_PL_REINFORCE; }
 
 __global__ void __launch_bounds__(256) bidrows_bucket_kernel(const BidFitParams p) {
   extern __shared__ int sm_i[];
@@ -46,7 +60,7 @@ __global__ void __launch_bounds__(256) bidrows_bucket_kernel(const BidFitParams 
   __syncthreads();
   for (long long j = threadIdx.x; j < NR; j += blockDim.x) {
     const uint32_t mt = meta[j];
-    if ((mt & kBidValid) && learns_winrate(p.bidder_kind[mt & 0xFFFu])) atomicAdd(&hist[mt & 0xFFFu], 1);
+    if ((mt & kBidValid) && p.fit_kind[mt & 0xFFFu] != AGYM_BFIT_NONE) atomicAdd(&hist[mt & 0xFFFu], 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -64,7 +78,7 @@ __global__ void __launch_bounds__(256) bidrows_bucket_kernel(const BidFitParams 
       int keyv = -1;
       if (j < NR) {
         const uint32_t mt = meta[j];
-        if ((mt & kBidValid) && learns_winrate(p.bidder_kind[mt & 0xFFFu])) keyv = int(mt & 0xFFFu);
+        if ((mt & kBidValid) && p.fit_kind[mt & 0xFFFu] != AGYM_BFIT_NONE) keyv = int(mt & 0xFFFu);
       }
       const unsigned peers = __match_any_sync(0xffffffffu, keyv);
       const int rank = __popc(peers & ((1u << lane) - 1u));
@@ -76,60 +90,152 @@ __global__ void __launch_bounds__(256) bidrows_bucket_kernel(const BidFitParams 
   }
 }
 
-__device__ __forceinline__ float clamp_log(float x) { return fmaxf(logf(x), -100.f); }  // BCELoss clamps its logs at -100
-
-__global__ void __launch_bounds__(256) winrate_fit_kernel(const BidFitParams p) {
-  constexpr int NT = 256, NW = NT / 32;
-  extern __shared__ __align__(16) float4 srow[];  // [ncap] {est, value, gamma, won}
-  __shared__ float red[2][NW][5];
+// Agent.update's gathering of the logged arrays (Agent.py:81-90) + the utilities of Bidder.py:219-220,371-372,479-480
+__global__ void __launch_bounds__(256) gather_rows_kernel(const BidFitParams p) {
   __shared__ int wins_s;
   const int run = blockIdx.x / p.A, a = blockIdx.x % p.A;
-  if (!learns_winrate(p.bidder_kind[a])) return;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int kind = p.fit_kind[a];
+  if (kind == AGYM_BFIT_NONE) return;
   const int* __restrict__ aoff = p.aoff + (size_t)run * (p.A + 1);
   const int row0 = aoff[a], n = aoff[a + 1] - row0;
-  double* __restrict__ bd = p.bidder_d + ((size_t)run * p.A + a) * AGYM_BIDDER_D;
-  float* __restrict__ bw = p.bidder_w + ((size_t)run * p.A + a) * AGYM_BIDDER_W;
-  float* info = p.info ? p.info + ((size_t)run * p.A + a) * 4 : nullptr;
-  // ---- stage the agent's rows ----
-  if (tid == 0) wins_s = 0;
+  if (threadIdx.x == 0) wins_s = 0;
   __syncthreads();
   const uint32_t* __restrict__ idx = p.srt_idx + (size_t)run * p.Tcap * p.P + row0;
   const uint32_t* __restrict__ meta = p.meta + (size_t)run * p.Tcap * p.P;
   const float* __restrict__ rows = p.rows + (size_t)run * p.Tcap * p.P * AGYM_BID_ROW;
-  float4* __restrict__ spill = p.spill + (size_t)run * p.Tcap * p.P + row0;
-  int my_wins = 0;
-  for (int j = tid; j < n; j += NT) {
-    const uint32_t r = idx[j];
-    const float* __restrict__ src = rows + (size_t)r * AGYM_BID_ROW;
-    const bool won = (meta[r] & kBidWon) != 0;
-    my_wins += won;
-    const float4 v = make_float4(src[0], src[1], src[2], won ? 1.f : 0.f);
-    if (j < p.ncap) srow[j] = v; else spill[j] = v;
+  float4* __restrict__ out = reinterpret_cast<float4*>(p.crow + ((size_t)run * p.Tcap * p.P + row0) * kRowF);
+  int my = 0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const uint32_t r = idx[j], mt = meta[r];
+    const float* __restrict__ s = rows + (size_t)r * AGYM_BID_ROW;
+    const bool won = (mt & kBidWon) != 0;
+    my += won;
+    const float util = won ? ((mt & kBidClick) ? s[1] : 0.0f) - s[4] : 0.0f;  // value * outcome - price on won rows
+    out[2 * j] = make_float4(s[0], s[1], s[2], fmaxf(s[3], 1e-15f));            // propensities clipped at 1e-15 (Bidder.py:385,571)
+    out[2 * j + 1] = make_float4(util, won ? 1.f : 0.f, 0.f, 0.f);
   }
-  if (my_wins) atomicAdd(&wins_s, my_wins);
+  if (my) atomicAdd(&wins_s, my);
   __syncthreads();
-  if (wins_s == 0) {  // Bidder.py:213-216 -- lost every auction: fall back to the un-shaded Gaussian logging policy
-    if (tid == 0) {
-      bd[2] = 0.0;
-      if (info) { info[0] = -1.f; info[1] = 0.f; info[2] = CUDART_NAN_F; info[3] = float(n); }
+  if (threadIdx.x == 0) {
+    int w = wins_s;
+    if (w == 0 && (kind == AGYM_BFIT_VL_SEARCH || kind == AGYM_BFIT_VL_POLICY)) {
+      // Bidder.py:213-216 -- lost every auction: fall back to the Gaussian logging policy, fit nothing
+      p.bidder_d[((size_t)run * p.A + a) * AGYM_BIDDER_D + 2] = 0.0;
+      w = -1;
+      if (p.info) { float* f = p.info + ((size_t)run * p.A + a) * 12; f[0] = -1.f; f[1] = 0.f; f[2] = CUDART_NAN_F; f[3] = float(n); }
     }
-    return;
+    p.wins[(size_t)run * p.A + a] = w;
   }
-  float w[4], ea[4] = {0, 0, 0, 0}, es[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};
+}
+
+__device__ __forceinline__ float clamp_log(float x) { return fmaxf(logf(x), -100.f); }  // BCELoss clamps its logs at -100
+__device__ __forceinline__ float sigmoidf_rn(float z) { return __fdiv_rn(1.0f, 1.0f + expf(-z)); }
+__device__ __forceinline__ float softplusf(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // torch.nn.Softplus(beta=1, threshold=20)
+__device__ __forceinline__ float dsoftplusf(float x) { return x > 20.f ? 1.f : sigmoidf_rn(x); }
+
+template <int NV, int NT>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* red /*[2][NT/32][NV]*/, int epoch, int tid) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+  }
+  float* r = red + (size_t)(epoch & 1) * (NT / 32) * NV;
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) r[(tid >> 5) * NV + k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) t += r[w * NV + k];
+    v[k] = t;
+  }
+}
+
+// Adam(weight_decay, amsgrad=True), ReduceLROnPlateau('min') and the "no 1e-6 improvement for `stop_after` epochs" rule
+// of the reference's training loops, replicated in every thread (all inputs are block-uniform).
+template <int NPAR>
+struct Trainer {
+  float ea[NPAR], es[NPAR], mx[NPAR];
+  double lr, wd, best_sched = INFINITY, best_loss = INFINITY, factor, min_lr, threshold;
+  int bad = 0, best_epoch = -1, patience, stop_after;
+  bool use_sched;
+  __device__ Trainer(double lr_, double wd_, bool sched, int patience_, double factor_, double min_lr_, double threshold_, int stop_after_)
+      : lr(lr_), wd(wd_), factor(factor_), min_lr(min_lr_), threshold(threshold_), patience(patience_), stop_after(stop_after_), use_sched(sched) {
+#pragma unroll
+    for (int k = 0; k < NPAR; ++k) ea[k] = es[k] = mx[k] = 0.f;
+  }
+  __device__ __forceinline__ void adam(float (&w)[NPAR], const float* grad, double bc1, float bc2s) {
+    const float alpha = float(-(lr / bc1)), wdf = float(wd);
+#pragma unroll
+    for (int k = 0; k < NPAR; ++k) {
+      const float g = fmaf(wdf, w[k], grad[k]);
+      ea[k] = fmaf(g - ea[k], 0.1f, ea[k]);
+      es[k] = fmaf(0.001f * g, g, es[k] * 0.999f);
+      mx[k] = fmaxf(mx[k], es[k]);
+      w[k] += __fdiv_rn(alpha * ea[k], __fdiv_rn(__fsqrt_rn(mx[k]), bc2s) + 1e-8f);
+    }
+  }
+  // returns true when training stops at this epoch
+  __device__ __forceinline__ bool after_epoch(double cur, int epoch) {
+    if (use_sched) {
+      if (cur < best_sched * (1.0 - threshold)) { best_sched = cur; bad = 0; } else { ++bad; }
+      if (bad > patience) {
+        const double new_lr = fmax(lr * factor, min_lr);
+        if (lr - new_lr > 1e-8) lr = new_lr;
+        bad = 0;
+      }
+    }
+    if (best_loss - cur > 1e-6) { best_epoch = epoch; best_loss = cur; return false; }
+    return epoch - best_epoch > stop_after;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// win-rate model (Models.py:51-62)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) winrate_fit_kernel(const BidFitParams p) {
+  constexpr int NT = 256;
+  extern __shared__ __align__(16) float4 srow[];  // [ncap] {est, value, gamma, won}
+  __shared__ float red[2 * (NT / 32) * 5];
+  const int run = blockIdx.x / p.A, a = blockIdx.x % p.A;
+  const int kind = p.fit_kind[a];
+  if (!fits_winrate(kind)) return;
+  if (p.wins[(size_t)run * p.A + a] < 0) return;
+  const int tid = threadIdx.x;
+  const int* __restrict__ aoff = p.aoff + (size_t)run * (p.A + 1);
+  const int row0 = aoff[a], n = aoff[a + 1] - row0;
+  if (n == 0) return;
+  double* __restrict__ bd = p.bidder_d + ((size_t)run * p.A + a) * AGYM_BIDDER_D;
+  float* __restrict__ bw = p.bidder_w + ((size_t)run * p.A + a) * AGYM_BIDDER_W;
+  float* info = p.info ? p.info + ((size_t)run * p.A + a) * 12 : nullptr;  // stage slot 0
+  float4* __restrict__ crow = reinterpret_cast<float4*>(p.crow + ((size_t)run * p.Tcap * p.P + row0) * kRowF);
+  for (int j = tid; j < n && j < p.ncap; j += NT) {
+    const float4 x = crow[2 * j], y = crow[2 * j + 1];
+    srow[j] = make_float4(x.x, x.y, x.z, y.y);
+  }
+  __syncthreads();
+  float w[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) w[k] = bw[k];
+  const bool dr = kind == AGYM_BFIT_DR;
+  // Bidder.py:242-243 (ValueLearning) / :520-521 (DoublyRobust)
+  Trainer<4> tr(3e-3, 1e-6, true, dr ? 256 : 100, dr ? 0.2 : 0.1, 1e-7, 1e-4, dr ? 1024 : 512);
   const float invN = 1.0f / float(2 * n);
-  double lr = 3e-3, best_sched = INFINITY, best_loss = INFINITY;
-  int bad = 0, best_epoch = -1, stop_epoch = -1, epochs_run = 0;
+  int stop_epoch = -1, epochs_run = 0;
   float last_loss = 0.f;
   for (int epoch = 0; epoch < p.max_epochs; ++epoch) {
     float part[5] = {0, 0, 0, 0, 0};  // loss, dL/dw0, dL/dw1, dL/dw2, dL/db  (sums; divided by N below)
     for (int j = tid; j < n; j += NT) {
-      const float4 r = j < p.ncap ? srow[j] : spill[j];
+      float4 r;
+      if (j < p.ncap) r = srow[j];
+      else { const float4 x = crow[2 * j], y = crow[2 * j + 1]; r = make_float4(x.x, x.y, x.z, y.y); }
       const float base = fmaf(r.y, w[1], fmaf(r.x, w[0], w[3]));
-      const float p1 = __fdiv_rn(1.0f, 1.0f + expf(-fmaf(r.z, w[2], base)));  // the logged row
-      const float p0 = __fdiv_rn(1.0f, 1.0f + expf(-base));                    // its gamma = 0 copy, labelled lost
+      const float p1 = sigmoidf_rn(fmaf(r.z, w[2], base));  // the logged row
+      const float p0 = sigmoidf_rn(base);                    // its gamma = 0 copy, labelled lost (Bidder.py:227-236)
       part[0] -= (r.w > 0.5f ? clamp_log(p1) : clamp_log(1.0f - p1)) + clamp_log(1.0f - p0);
       const float g1 = p1 - r.w, gs = g1 + p0;
       part[1] = fmaf(gs, r.x, part[1]);
@@ -137,64 +243,211 @@ __global__ void __launch_bounds__(256) winrate_fit_kernel(const BidFitParams p) 
       part[3] = fmaf(g1, r.z, part[3]);
       part[4] += gs;
     }
+    block_sum<5, NT>(part, red, epoch, tid);
+    const float loss = part[0] * invN;
+    float grad[4];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) part[k] += __shfl_xor_sync(0xffffffffu, part[k], off);
-    }
-    float(*r2)[5] = red[epoch & 1];
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) r2[wid][k] = part[k];
-    }
-    __syncthreads();
-    float tot[5] = {0, 0, 0, 0, 0};
-#pragma unroll
-    for (int v = 0; v < NW; ++v) {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) tot[k] += r2[v][k];
-    }
-    const float loss = tot[0] * invN;
-    // Adam with L2 weight decay and amsgrad (torch/optim/adam.py, single-tensor path)
-    const float alpha = float(-(lr / p.bc1[epoch]));
-    const float bc2s = p.bc2s[epoch];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float g = fmaf(1e-6f, w[k], tot[k + 1] * invN);
-      ea[k] = fmaf(g - ea[k], 0.1f, ea[k]);
-      es[k] = fmaf(0.001f * g, g, es[k] * 0.999f);
-      mx[k] = fmaxf(mx[k], es[k]);
-      w[k] += __fdiv_rn(alpha * ea[k], __fdiv_rn(__fsqrt_rn(mx[k]), bc2s) + 1e-8f);
-    }
+    for (int k = 0; k < 4; ++k) grad[k] = part[k + 1] * invN;
+    tr.adam(w, grad, p.bc1[epoch], p.bc2s[epoch]);
     epochs_run = epoch + 1;
     last_loss = loss;
-    const double cur = double(loss);
-    // ReduceLROnPlateau('min', patience=100, factor=0.1, min_lr=1e-7)  (Bidder.py:243)
-    if (cur < best_sched * (1.0 - 1e-4)) { best_sched = cur; bad = 0; } else { ++bad; }
-    if (bad > 100) {
-      const double new_lr = fmax(lr * 0.1, 1e-7);
-      if (lr - new_lr > 1e-8) lr = new_lr;
-      bad = 0;
+    if (tr.after_epoch(double(loss), epoch)) { stop_epoch = epoch; break; }
+  }
+  __syncthreads();
+  if (dr) {  // Bidder.py:545-551  u_hat = W (V - P) on the logged gammas
+    for (int j = tid; j < n; j += NT) {
+      const float4 x = crow[2 * j];
+      float4 y = crow[2 * j + 1];
+      const float W = sigmoidf_rn(fmaf(x.z, w[2], fmaf(x.y, w[1], fmaf(x.x, w[0], w[3]))));
+      const float V = x.x * x.y;
+      y.z = W * (V - V * x.z);
+      crow[2 * j + 1] = y;
     }
-    // Bidder.py:255-260
-    if (best_loss - cur > 1e-6) { best_epoch = epoch; best_loss = cur; }
-    else if (epoch - best_epoch > 512) { stop_epoch = epoch; break; }
   }
   if (tid == 0) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) bw[k] = w[k];
-    bd[2] = 1.0;  // model_initialised = True (Bidder.py:325)
+    if (kind == AGYM_BFIT_VL_SEARCH) bd[2] = 1.0;  // model_initialised = True (Bidder.py:325)
     if (info) { info[0] = float(stop_epoch); info[1] = float(epochs_run); info[2] = last_loss; info[3] = float(n); }
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Gaussian bid-shading policy (Models.py:65-218)
+// ------------------------------------------------------------------------------------------------
+struct PolicyFwd {
+  float h0, h1, s0, s1, a_mu, a_sg, mu, sg_raw, sigma;
+};
+
+__device__ __forceinline__ PolicyFwd policy_forward(const float (&th)[12], float x0, float x1) {
+  PolicyFwd f;
+  f.h0 = fmaf(x1, th[1], fmaf(x0, th[0], th[4]));
+  f.h1 = fmaf(x1, th[3], fmaf(x0, th[2], th[5]));
+  f.s0 = softplusf(f.h0);
+  f.s1 = softplusf(f.h1);
+  f.a_mu = fmaf(f.s1, th[7], fmaf(f.s0, th[6], th[8]));
+  f.a_sg = fmaf(f.s1, th[10], fmaf(f.s0, th[9], th[11]));
+  f.mu = softplusf(f.a_mu);
+  f.sg_raw = softplusf(f.a_sg);
+  f.sigma = f.sg_raw + 1e-2f;  // min_sigma (Models.py:80,104)
+  return f;
+}
+
+__device__ __forceinline__ void policy_backward(const float (&th)[12], const PolicyFwd& f, float x0, float x1, float d_mu, float d_sg,
+                                                float (&acc)[13]) {
+  const float d_amu = d_mu * dsoftplusf(f.a_mu), d_asg = d_sg * dsoftplusf(f.a_sg);
+  const float d_h0 = fmaf(d_asg, th[9], d_amu * th[6]) * dsoftplusf(f.h0);
+  const float d_h1 = fmaf(d_asg, th[10], d_amu * th[7]) * dsoftplusf(f.h1);
+  acc[1] = fmaf(d_h0, x0, acc[1]);
+  acc[2] = fmaf(d_h0, x1, acc[2]);
+  acc[3] = fmaf(d_h1, x0, acc[3]);
+  acc[4] = fmaf(d_h1, x1, acc[4]);
+  acc[5] += d_h0;
+  acc[6] += d_h1;
+  acc[7] = fmaf(d_amu, f.s0, acc[7]);
+  acc[8] = fmaf(d_amu, f.s1, acc[8]);
+  acc[9] += d_amu;
+  acc[10] = fmaf(d_asg, f.s0, acc[10]);
+  acc[11] = fmaf(d_asg, f.s1, acc[11]);
+  acc[12] += d_asg;
+}
+
+enum { kStageImitate = 0, kStageMain = 1 };
+
+__global__ void __launch_bounds__(256) policy_fit_kernel(const BidFitParams p) {
+  constexpr int NT = 256;
+  __shared__ float red[2 * (NT / 32) * 13];
+  const int run = blockIdx.x / p.A, a = blockIdx.x % p.A;
+  const int kind = p.fit_kind[a];
+  if (!fits_policy(kind)) return;
+  if (p.wins[(size_t)run * p.A + a] < 0) return;
+  double* __restrict__ bd = p.bidder_d + ((size_t)run * p.A + a) * AGYM_BIDDER_D;
+  const bool imitate = p.stage == kStageImitate;
+  if (imitate && (!needs_imitation(kind) || bd[2] != 0.0)) return;  // Bidder.py:381-382,567-568: first update only
+  const int tid = threadIdx.x;
+  const int* __restrict__ aoff = p.aoff + (size_t)run * (p.A + 1);
+  const int row0 = aoff[a], n = aoff[a + 1] - row0;
+  if (n == 0) return;
+  float* __restrict__ bw = p.bidder_w + ((size_t)run * p.A + a) * AGYM_BIDDER_W;
+  float* info = p.info ? p.info + ((size_t)run * p.A + a) * 12 + (p.stage == kStageImitate ? 4 : 8) : nullptr;
+  const float4* __restrict__ crow = reinterpret_cast<const float4*>(p.crow + ((size_t)run * p.Tcap * p.P + row0) * kRowF);
+  float th[12], ww[4];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) th[k] = bw[4 + k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ww[k] = bw[k];
+  // hyper-parameters: Models.py:113-115 | Bidder.py:283-286 | :389-392 | :575-578
+  double lr = 2e-3, wd = 1e-4, factor = 0.2, min_lr = 1e-8, threshold = 1e-4;
+  int stop_after = 512, cap = kAdamTable;
+  bool sched = true;
+  if (imitate) { lr = 1e-3; sched = false; }
+  else if (kind == AGYM_BFIT_VL_POLICY) { wd = 1e-6; factor = 0.1; min_lr = 1e-7; stop_after = 256; }
+  else if (kind == AGYM_BFIT_DR) { lr = 7e-3; threshold = 5e-3; cap = kAdamTable2; }
+  Trainer<12> tr(lr, wd, sched, 100, factor, min_lr, threshold, stop_after);
+  const int max_epochs = p.max_epochs > 0 && p.max_epochs < cap ? p.max_epochs : cap;
+  const float invn = 1.0f / float(n);
+  const PhiloxKey key = make_key(p.seed, uint32_t(p.run_offset + run));
+  const float lo = 1.0f / 50.0f, hi = 50.0f;  // importance_weight_clipping_eps = 50 (Bidder.py:398,584)
+  int stop_epoch = -1, epochs_run = 0;
+  float last_loss = 0.f;
+  bool nan_seen = false;
+  for (int epoch = 0; epoch < max_epochs; ++epoch) {
+    float acc[13];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) acc[k] = 0.f;
+    for (int j = tid; j < n; j += NT) {
+      const float4 x = crow[2 * j], y = crow[2 * j + 1];  // {est, value, gamma, prop}, {utility, won, u_hat, -}
+      const PolicyFwd f = policy_forward(th, x.x, x.y);
+      float d_mu = 0.f, d_sg = 0.f;
+      if (imitate) {  // Models.py:122-124: MSE(mu, gamma) + MSE(sigma without min_sigma, 0.05)
+        const float e_mu = f.mu - x.z, e_sg = f.sg_raw - 0.05f;
+        acc[0] = fmaf(e_mu, e_mu, fmaf(e_sg, e_sg, acc[0]));
+        d_mu = 2.0f * e_mu;
+        d_sg = 2.0f * e_sg;
+      } else {
+        float t = 0.f, dt_dmu = 0.f, dt_dsg = 0.f, iw = 0.f;
+        if (kind != AGYM_BFIT_VL_POLICY) {  // normal_pdf (Models.py:157-165), clipped at 1e-30
+          const float dm = f.mu - x.z, inv_s = __fdiv_rn(1.0f, f.sigma), z = dm * inv_s;
+          const float t_raw = expf(-0.5f * z * z) * inv_s * 0.3989422804014327f;
+          if (t_raw > 1e-30f) {
+            t = t_raw;
+            dt_dmu = -t * dm * inv_s * inv_s;
+            dt_dsg = t * (dm * dm * inv_s * inv_s * inv_s - inv_s);
+          } else {
+            t = 1e-30f;
+          }
+          iw = __fdiv_rn(t, x.w);
+        }
+        const float u = y.x;
+        if (kind == AGYM_BFIT_PL_REINFORCE) {            // Models.py:173-174
+          acc[0] -= t * u;
+          d_mu = -u * dt_dmu; d_sg = -u * dt_dsg;
+        } else if (kind == AGYM_BFIT_PL_OFFPOLICY) {     // Models.py:176-178
+          acc[0] -= iw * u;
+          const float c = -__fdiv_rn(u, x.w);
+          d_mu = c * dt_dmu; d_sg = c * dt_dsg;
+        } else if (kind == AGYM_BFIT_PL_TRPO) {          // Models.py:180-187, KL_weight 5e-2
+          const float dm = f.mu - x.z, s2 = f.sigma * f.sigma;
+          acc[0] += 0.05f * (__fdiv_rn(s2 + dm * dm, 2.0f * s2) - 0.5f) - iw * u;
+          const float c = -__fdiv_rn(u, x.w);
+          d_mu = fmaf(c, dt_dmu, 0.05f * __fdiv_rn(dm, s2));
+          d_sg = fmaf(c, dt_dsg, -0.05f * __fdiv_rn(dm * dm, s2 * f.sigma));
+        } else if (kind == AGYM_BFIT_PL_PPO) {           // Models.py:189-196
+          const float cl = fminf(fmaxf(iw, lo), hi);
+          acc[0] -= fminf(iw * u, cl * u);
+          const bool pass = (iw >= lo && iw <= hi) || (iw > hi && u < 0.f) || (iw < lo && u > 0.f);
+          const float c = pass ? -__fdiv_rn(u, x.w) : 0.f;
+          d_mu = c * dt_dmu; d_sg = c * dt_dsg;
+        } else {                                         // Doubly Robust (Models.py:198-218) / 'policy' (Bidder.py:292-302)
+          const float eps = philox_normal4(uint32_t(j), uint32_t(epoch), (6u << 16) | uint32_t(a), uint32_t(p.iter), key).x;
+          const float raw = fmaf(f.sigma, eps, f.mu);
+          const float gs = fminf(fmaxf(raw, 0.f), 1.f);
+          const float W = sigmoidf_rn(fmaf(gs, ww[2], fmaf(x.y, ww[1], fmaf(x.x, ww[0], ww[3]))));
+          const float V = x.x * x.y;
+          acc[0] -= W * (V - V * gs);
+          if (raw > 0.f && raw < 1.f) {
+            const float dd = -V * (W * (1.0f - W) * ww[2] * (1.0f - gs) - W);
+            d_mu = dd; d_sg = dd * eps;
+          }
+          if (kind == AGYM_BFIT_DR) {
+            const float du = u - y.z, cl = fminf(fmaxf(iw, lo), hi);
+            acc[0] -= du * cl;
+            if (iw >= lo && iw <= hi) {
+              const float c = -__fdiv_rn(du, x.w);
+              d_mu = fmaf(c, dt_dmu, d_mu); d_sg = fmaf(c, dt_dsg, d_sg);
+            }
+          }
+        }
+      }
+      policy_backward(th, f, x.x, x.y, d_mu, d_sg, acc);
+    }
+    block_sum<13, NT>(acc, red, epoch, tid);
+    const float loss = acc[0] * invn;
+    float grad[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) grad[k] = acc[k + 1] * invn;
+    tr.adam(th, grad, p.bc1[epoch], p.bc2s[epoch]);
+    epochs_run = epoch + 1;
+    last_loss = loss;
+    nan_seen |= !(loss == loss);
+    if (tr.after_epoch(double(loss), epoch)) { stop_epoch = epoch; break; }
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) bw[4 + k] = th[k];
+    if (!imitate) bd[2] = 1.0;  // model_initialised = True (Bidder.py:325,430,614)
+    if (info) { info[0] = float(stop_epoch); info[1] = float(epochs_run); info[2] = nan_seen ? CUDART_NAN_F : last_loss; info[3] = float(n); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 size_t bidder_workspace_bytes(const agym_handle* h, int64_t Tcap) {
   const agym_shape& s = h->shape;
   const size_t NR = (size_t)s.R * Tcap * s.P;
-  return NR * sizeof(uint32_t) + (size_t)s.R * (s.A + 1) * sizeof(int) + 256 + NR * sizeof(float4) + 256;
+  return NR * sizeof(uint32_t) + (size_t)s.R * (s.A + 1) * sizeof(int) + (size_t)s.R * s.A * sizeof(int) + NR * kRowF * sizeof(float) + 1024;
 }
 
-int launch_update_bidders(agym_handle* h, int max_epochs, float* fit_info, cudaStream_t s) {
+int launch_update_bidders(agym_handle* h, uint64_t seed, int iter, int max_epochs, float* fit_info, cudaStream_t s) {
   const agym_shape& sh = h->shape;
   const int64_t Tn = h->rounds_in_iter;
   if (Tn <= 0) return AGYM_OK;
@@ -203,31 +456,47 @@ int launch_update_bidders(agym_handle* h, int max_epochs, float* fit_info, cudaS
   BidFitParams bp{};
   bp.R = sh.R; bp.A = sh.A; bp.P = sh.P;
   bp.Tcap = h->bid_Tcap; bp.Tn = Tn;
-  bp.bidder_kind = h->d_bidder_kind;
+  bp.fit_kind = h->d_bidder_fit;
   bp.rows = h->bid_rows; bp.meta = h->bid_meta;
   const size_t NR = (size_t)sh.R * h->bid_Tcap * sh.P;
-  unsigned char* w = static_cast<unsigned char*>(h->bws);
-  w = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(w) + 255) & ~uintptr_t(255));
-  bp.srt_idx = reinterpret_cast<uint32_t*>(w); w += NR * sizeof(uint32_t);
-  bp.aoff = reinterpret_cast<int*>(w); w += (size_t)sh.R * (sh.A + 1) * sizeof(int);
-  w = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(w) + 255) & ~uintptr_t(255));
-  bp.spill = reinterpret_cast<float4*>(w);
+  auto align = [](unsigned char* w) { return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(w) + 255) & ~uintptr_t(255)); };
+  unsigned char* w = align(static_cast<unsigned char*>(h->bws));
+  bp.srt_idx = reinterpret_cast<uint32_t*>(w); w = align(w + NR * sizeof(uint32_t));
+  bp.aoff = reinterpret_cast<int*>(w); w = align(w + (size_t)sh.R * (sh.A + 1) * sizeof(int));
+  bp.wins = reinterpret_cast<int*>(w); w = align(w + (size_t)sh.R * sh.A * sizeof(int));
+  bp.crow = reinterpret_cast<float*>(w);
   bp.bidder_d = h->bidder_d; bp.bidder_w = h->bidder_w;
   bp.info = fit_info;
   bp.bc1 = h->d_adam_bc1; bp.bc2s = h->d_adam_bc2s2;
-  bp.max_epochs = max_epochs > 0 ? max_epochs : kAdamTable2;  // Bidder.py:240  epochs = 8192 * 4
+  bp.max_epochs = max_epochs;
+  bp.run_offset = sh.run_offset; bp.seed = seed; bp.iter = iter;
+  const unsigned grid = unsigned(sh.R) * unsigned(sh.A);
   bidrows_bucket_kernel<<<sh.R, 256, (2 * sh.A + 1) * sizeof(int), s>>>(bp);
-  int rc = check_cuda(h, cudaGetLastError(), "bidrows_bucket_kernel");
+  gather_rows_kernel<<<grid, 256, 0, s>>>(bp);
+  int rc = check_cuda(h, cudaGetLastError(), "bidder fit prologue");
   if (rc) return rc;
-  long long ncap = 2 * (Tn * sh.P / sh.A) + 64;  // expected rows per agent x 2
-  if (ncap > Tn * sh.P) ncap = Tn * sh.P;
-  if (ncap > 12000) ncap = 12000;  // 192 KB of float4
-  bp.ncap = int(ncap);
-  const size_t smem = (size_t)bp.ncap * sizeof(float4);
-  cudaError_t e = cudaFuncSetAttribute(winrate_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  if (e != cudaSuccess) return check_cuda(h, e, "winrate_fit_kernel attribute");
-  winrate_fit_kernel<<<unsigned(sh.R) * unsigned(sh.A), 256, smem, s>>>(bp);
-  return check_cuda(h, cudaGetLastError(), "winrate_fit_kernel");
+  if (h->any_winrate_fit) {
+    long long ncap = 2 * (Tn * sh.P / sh.A) + 64;  // expected rows per agent x 2
+    if (ncap > Tn * sh.P) ncap = Tn * sh.P;
+    if (ncap > 12000) ncap = 12000;  // 192 KB of float4
+    BidFitParams wp = bp;
+    wp.ncap = int(ncap);
+    wp.max_epochs = max_epochs > 0 && max_epochs < kAdamTable2 ? max_epochs : kAdamTable2;  // Bidder.py:240  epochs = 8192 * 4
+    const size_t smem = (size_t)wp.ncap * sizeof(float4);
+    cudaError_t e = cudaFuncSetAttribute(winrate_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return check_cuda(h, e, "winrate_fit_kernel attribute");
+    winrate_fit_kernel<<<grid, 256, smem, s>>>(wp);
+    if ((rc = check_cuda(h, cudaGetLastError(), "winrate_fit_kernel"))) return rc;
+  }
+  if (h->any_policy_fit) {
+    BidFitParams pp = bp;
+    pp.stage = kStageImitate;
+    policy_fit_kernel<<<grid, 256, 0, s>>>(pp);
+    pp.stage = kStageMain;
+    policy_fit_kernel<<<grid, 256, 0, s>>>(pp);
+    if ((rc = check_cuda(h, cudaGetLastError(), "policy_fit_kernel"))) return rc;
+  }
+  return AGYM_OK;
 }
 
 }  // namespace agym

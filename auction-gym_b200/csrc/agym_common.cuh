@@ -185,6 +185,9 @@ struct agym_handle {
   int* d_n_items = nullptr;
   int* d_alloc_kind = nullptr;
   int* d_bidder_kind = nullptr;
+  int* d_bidder_fit = nullptr;
+  int bidder_fit_host[4096];
+  bool any_winrate_fit = false, any_policy_fit = false, any_unassigned_bandit = false;
   double* d_E64 = nullptr;
   double* d_V64 = nullptr;
   float* d_E32 = nullptr;
@@ -228,7 +231,7 @@ int launch_simulate(agym_handle* h, const SimParams& p, const agym_replay_inputs
 int launch_refresh_sigma(agym_handle* h, cudaStream_t s);
 int launch_update_allocators(agym_handle* h, int fit_mode, int max_epochs, float* fit_info, cudaStream_t s);
 size_t fit_workspace_bytes(const agym_handle* h, int64_t Tcap);
-int launch_update_bidders(agym_handle* h, int max_epochs, float* fit_info, cudaStream_t s);
+int launch_update_bidders(agym_handle* h, uint64_t seed, int iter, int max_epochs, float* fit_info, cudaStream_t s);
 size_t bidder_workspace_bytes(const agym_handle* h, int64_t Tcap);
 int launch_k1(agym_handle* h, const SimParams& p, float* ctx, uint8_t* parts, cudaStream_t s);
 int launch_k2(agym_handle* h, const SimParams& p, const float* ctx, const uint8_t* parts, uint8_t* item, float* est,

@@ -212,6 +212,28 @@ __device__ __forceinline__ Real shade_bid(const SimParams& p, int run, int a, in
       prop = exp(-(q_ * q_) / Real(2)) / (sg * Real(2.5066282746310002));  // Bidder.py:178
     }
     bid = bid * gamma;
+  } else if (eff == AGYM_BID_BANDIT || eff == AGYM_BID_POLICY) {
+    // BidShadingContextualBandit.forward / BidShadingPolicy.forward (Models.py:82-90,146-155): float32 throughout
+    using A_ = Arith<Real>;
+    const float* __restrict__ th = p.bidder_w + ((size_t)run * p.A + a) * AGYM_BIDDER_W + 4;
+    const float x0 = float(est), x1 = float(value);
+    const float h0 = A_::mac(x1, th[1], A_::mac(x0, th[0], 0.0f)) + th[4];
+    const float h1 = A_::mac(x1, th[3], A_::mac(x0, th[2], 0.0f)) + th[5];
+    const float s0 = h0 > 20.f ? h0 : log1pf(expf(h0)), s1 = h1 > 20.f ? h1 : log1pf(expf(h1));
+    const float amu = A_::mac(s1, th[7], A_::mac(s0, th[6], 0.0f)) + th[8];
+    const float asg = A_::mac(s1, th[10], A_::mac(s0, th[9], 0.0f)) + th[11];
+    const float mu = amu > 20.f ? amu : log1pf(expf(amu));
+    const float sg = (asg > 20.f ? asg : log1pf(expf(asg))) + 1e-2f;
+    float eps;
+    if (replay) eps = float(gamma_z_replay);
+    else eps = philox_normal4(rc.c0, rc.c1, (kPurposeGamma << 16) | uint32_t(s), 0u, key).x;
+    const float raw = __fadd_rn(mu, __fmul_rn(eps, sg));                 // rsample: loc + eps * scale
+    const float dv = raw - mu;
+    const float logp = -(dv * dv) / (2.0f * (sg * sg)) - logf(sg) - 0.9189385332046727f;  // Normal.log_prob
+    prop = Real(expf(logp));
+    const float gcl = fminf(fmaxf(raw, 0.0f), 1.0f);                     // torch.clip(sampled_value, 0, 1)
+    gamma = Real(gcl);
+    bid = bid * gamma;
   }
   return bid;
 }

@@ -35,7 +35,7 @@ class Engine:
     """
 
     def __init__(self, *, R, A, I, D, Do, P, mechanism, E, V, n_items, alloc_kind, bidder_kind, embedding_var=1.0,
-                 precision=_lib.FP32, device=0, run_offset=0, rounds_capacity=0):
+                 precision=_lib.FP32, device=0, run_offset=0, rounds_capacity=0, bidder_fit=None):
         if not torch.cuda.is_available():
             raise AgymError("CUDA device required: the AuctionGym B200 engine has no CPU fallback")
         self.lib = _lib.load()
@@ -55,6 +55,10 @@ class Engine:
         assert self.n_items.shape == (self.A,) and self.alloc_kind.shape == (self.A,) and self.bidder_kind.shape == (self.A,)
         self._check(self.lib.agym_set_agents(self.handle, self.n_items.ctypes.data, self.alloc_kind.ctypes.data,
                                              self.bidder_kind.ctypes.data))
+        if bidder_fit is not None:  # which Bidder.update each agent runs (only needed for AGYM_BID_BANDIT agents)
+            self.bidder_fit = np.ascontiguousarray(bidder_fit, np.int32)
+            assert self.bidder_fit.shape == (self.A,)
+            self._check(self.lib.agym_set_bidder_fits(self.handle, self.bidder_fit.ctypes.data))
         E = np.ascontiguousarray(E, np.float64)
         V = np.ascontiguousarray(V, np.float64)
         assert E.shape == (self.A, self.I, self.D + 1) and V.shape == (self.A, self.I), (E.shape, V.shape)
@@ -238,12 +242,14 @@ class Engine:
         self._check(self.lib.agym_update_allocators(self.handle, int(fit_mode), int(max_epochs), _ptr(info), self._stream()))
         return info
 
-    def update_bidders(self, max_epochs=0, want_info=True):
-        """Agent.update -> bidder.update for every (run, agent) whose bidder learns (Bidder.py:210-325)."""
+    def update_bidders(self, seed=0, iteration=0, max_epochs=0, want_info=True):
+        """Agent.update -> bidder.update for every (run, agent) whose bidder learns (Bidder.py:210-325,369-431,477-615).
+        Returns fit_info [R, A, 3, 4]: per stage (win-rate, initialise_policy, policy) {stop epoch, epochs, loss, rows}."""
         if not self.learning_bidders:
             return None
-        info = torch.zeros((self.R, self.A, 4), dtype=torch.float32, device=self.device) if want_info else None
-        self._check(self.lib.agym_update_bidders(self.handle, int(max_epochs), _ptr(info), self._stream()))
+        info = torch.zeros((self.R, self.A, 3, 4), dtype=torch.float32, device=self.device) if want_info else None
+        self._check(self.lib.agym_update_bidders(self.handle, C.c_uint64(int(seed) & (2**64 - 1)), int(iteration), int(max_epochs),
+                                                 _ptr(info), self._stream()))
         return info
 
     # ------------------------------------------------------------------ staged kernels

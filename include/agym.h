@@ -185,13 +185,25 @@ int agym_update_allocators(agym_handle* h, int32_t fit_mode, int32_t max_epochs,
 int agym_bind_bid_log(agym_handle* h, float* bid_rows, uint32_t* bid_meta, int64_t Tcap);
 size_t agym_bidder_workspace_bytes(const agym_handle* h, int64_t Tcap);
 int agym_bind_bidder_workspace(agym_handle* h, void* ws, size_t bytes);
-/* Bidder.update for every (run, agent) whose bidder learns (Bidder.py:210-325).  Built so far:
- * ValueLearningBidder(inference='search'): the win-rate model P(win | CTR, value, gamma) fitted with
- * Adam(lr 3e-3, weight_decay 1e-6, amsgrad) + ReduceLROnPlateau(patience 100, factor 0.1, min_lr 1e-7) on the logged
- * rows plus the gamma = 0 augmentation, early stop after 512 epochs without a 1e-6 improvement; sets `initialised`
- * (or clears it when the agent won nothing, Bidder.py:213-216).  Other learning bidders return AGYM_ERR_UNSUPPORTED.
- * fit_info (device, nullable) [R][A][4] float: {stop_epoch or -1, epochs run, final loss, rows}. */
-int agym_update_bidders(agym_handle* h, int32_t max_epochs, float* fit_info, void* stream);
+/* What bidder.update does for each agent (Bidder.py).  agym_set_agents derives VL_SEARCH / VL_POLICY from the bid kinds
+ * AGYM_BID_SEARCH / AGYM_BID_POLICY; agents that bid with AGYM_BID_BANDIT must be told which bidder they are. */
+enum agym_bidder_fit {
+  AGYM_BFIT_NONE = 0,
+  AGYM_BFIT_VL_SEARCH = 1,     /* ValueLearningBidder('search'): win-rate fit                      Bidder.py:210-260 */
+  AGYM_BFIT_VL_POLICY = 2,     /* ValueLearningBidder('policy'): win-rate fit + policy fit         Bidder.py:278-316 */
+  AGYM_BFIT_PL_REINFORCE = 3,  /* PolicyLearningBidder(loss=...)                                   Bidder.py:369-431 */
+  AGYM_BFIT_PL_OFFPOLICY = 4,
+  AGYM_BFIT_PL_TRPO = 5,
+  AGYM_BFIT_PL_PPO = 6,
+  AGYM_BFIT_DR = 7             /* DoublyRobustBidder                                               Bidder.py:477-615 */
+};
+int agym_set_bidder_fits(agym_handle* h, const int32_t* fit_kind /* [A], host */);
+/* Agent.update -> bidder.update for every (run, agent) whose bidder learns: win-rate fit, initialise_policy on the
+ * first update, then the bidder's policy loss; sets the per-(run, agent) `initialised` flag (ValueLearning bidders that
+ * won nothing clear it instead, Bidder.py:213-216).  (seed, iter) key the rsample noise of the stochastic losses.
+ * fit_info (device, nullable) [R][A][3][4] float: per stage {win-rate, initialise_policy, policy} the tuple
+ * {stop_epoch or -1, epochs run, final loss (NaN if any loss was NaN, cf. Bidder.py:412-419), rows}. */
+int agym_update_bidders(agym_handle* h, uint64_t seed, int32_t iter, int32_t max_epochs, float* fit_info, void* stream);
 
 /* ---- staged kernels (intermediates in HBM; used for roofline evidence and isolation tests) ---- */
 /* K1  Auction.py:33,42: contexts [N][D] float and participants [N][P] uint8 for N = n_runs*T opportunities */

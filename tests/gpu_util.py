@@ -24,10 +24,11 @@ def engine_from_case(case, R=1, precision=_lib.FP64, run_offset=0, rounds_capaci
         q = np.broadcast_to(case["q"], (R,) + case["q"].shape)
         eng.set_allocator_state(np.ascontiguousarray(m), np.ascontiguousarray(q))
     if eng.any_shaded:
-        searching = np.asarray(case["bidder_kind"]) == ao.BID_SEARCH  # fixtures with BID_SEARCH hold a fitted win-rate model
+        fitted = np.isin(np.asarray(case["bidder_kind"]), [ao.BID_SEARCH, ao.BID_BANDIT, ao.BID_POLICY])  # fixtures hold fitted models
         eng.set_bidder_state(case["bidder_f"][:, 0][None, :], case["bidder_f"][:, 1][None, :],
-                             initialised=searching[None, :].astype(np.float64),
-                             winrate_w=case["winrate_w"][None] if "winrate_w" in case else None)
+                             initialised=fitted[None, :].astype(np.float64),
+                             winrate_w=case["winrate_w"][None] if "winrate_w" in case else None,
+                             policy_w=case["policy_w"][None] if "policy_w" in case else None)
     return eng
 
 

@@ -15,7 +15,7 @@ RTOL_F64 = 1e-11            # float64 arithmetic (Oracle path, prices, utilities
 RTOL_F32_EST = 2e-6         # float32 CTR estimates (learnt path): a few ulp
 
 
-def compare_rounds(got, want, margins, *, rtol, est_rtol, max_tie_frac=0.01, what=""):
+def compare_rounds(got, want, margins, *, rtol, est_rtol, max_tie_frac=0.01, what="", gamma_rtol=None, prop_rtol=None):
     """Compare per-(round, slot) records.
 
     got / want: dicts with item, winner, outcome, won, est, value, bid, true_ctr, best_ev, price, second.
@@ -41,11 +41,11 @@ def compare_rounds(got, want, margins, *, rtol, est_rtol, max_tie_frac=0.01, wha
                    ("bid", est_rtol), ("price", est_rtol), ("second", est_rtol)):
         np.testing.assert_allclose(np.asarray(got[k])[ok], np.asarray(want[k])[ok], rtol=tol, atol=tol * 1e-3,
                                    err_msg=f"{what}: {k}")
-    for k in ("gamma", "propensity"):
+    for k, tol in (("gamma", gamma_rtol), ("propensity", prop_rtol)):
         if k in got and k in want:
             g, w = np.asarray(got[k])[ok], np.asarray(want[k])[ok]
             assert np.array_equal(np.isnan(g), np.isnan(w)), f"{what}: {k} NaN pattern"
-            np.testing.assert_allclose(np.nan_to_num(g), np.nan_to_num(w), rtol=max(rtol, 1e-9), atol=1e-300, err_msg=f"{what}: {k}")
+            np.testing.assert_allclose(np.nan_to_num(g), np.nan_to_num(w), rtol=tol or max(rtol, 1e-9), atol=1e-300, err_msg=f"{what}: {k}")
     return {"rounds": T, "near_tie_rounds": n_tie, "min_item_margin": float(margins["item_margin"].min()),
             "min_bid_margin": float(np.min(margins["bid_margin"]))}
 

@@ -63,7 +63,7 @@ def test_winrate_fit_matches_reference_and_oracle():
     eng, torch = _engine(len(agents), len(recs), w0)
     n = _fill(eng, torch, 0, recs)
     eng._check(eng.lib.agym_set_rounds_in_iteration(eng.handle, n))
-    info = eng.update_bidders().cpu().numpy()[0]
+    info = eng.update_bidders().cpu().numpy()[0, :, 0]
     w1 = eng.bidder_w.cpu().numpy()[0, :, :4]
     init = eng.bidder_d.cpu().numpy()[0, :, 2]
     for j, a in enumerate(agents):
@@ -93,7 +93,7 @@ def test_winrate_fit_fixed_budget_against_oracle_and_no_win_fallback():
     eng.bidder_d[0, 1, 2] = 1.0  # agent 1 had a fitted model before
     n = _fill(eng, torch, 0, recs)
     eng._check(eng.lib.agym_set_rounds_in_iteration(eng.handle, n))
-    info = eng.update_bidders(max_epochs=600).cpu().numpy()[0]
+    info = eng.update_bidders(max_epochs=600).cpu().numpy()[0, :, 0]
     orc = fo.fit_winrate(z[f"a{a}_est"], z[f"a{a}_value"], z[f"a{a}_gamma"], z[f"a{a}_won"], z[f"a{a}_w0"], max_epochs=600)
     w1 = eng.bidder_w.cpu().numpy()[0, :, :4]
     init = eng.bidder_d.cpu().numpy()[0, :, 2]
@@ -103,4 +103,96 @@ def test_winrate_fit_fixed_budget_against_oracle_and_no_win_fallback():
     assert init.tolist() == [1.0, 0.0, 0.0]                      # Bidder.py:213-216 fallback for the agent that won nothing
     assert np.array_equal(w1[1], z[f"a{a}_w0"]) and info[1, 3] == 50 and info[1, 1] == 0
     assert np.array_equal(w1[2], z[f"a{a}_w0"]) and info[2, 3] == 0  # an agent that never participated: untouched
+    eng.close()
+
+
+def test_policy_learning_bidder_fit_matches_reference():
+    """PolicyLearningBidder.update (Bidder.py:369-431): initialise_policy then the PPO fit, on rows the reference logged.
+    The PPO objective has flat directions (the reference's own parameters move by 1e-2..2e-1 between equivalent runs of
+    the oracle), so the bar is on what the policy computes -- mu and sigma on the logged contexts -- not on raw weights."""
+    _gpu()
+    import torch
+
+    import auction_gym_b200 as ag
+    from auction_gym_b200 import _lib
+    from oracle import policy_oracle as po
+
+    z = np.load(f"{GOLDEN_DIR}/bidfit_ppo.npz")
+    nA = 3
+    per = {a: list(zip(z[f"a{a}_est"], z[f"a{a}_value"], z[f"a{a}_gamma"], z[f"a{a}_prop"], z[f"a{a}_utility"], z[f"a{a}_won"])) for a in range(nA)}
+    recs = []
+    for k in range(max(len(v) for v in per.values())):
+        for a in range(nA):
+            if k < len(per[a]):
+                recs.append((a,) + tuple(per[a][k]))
+    T = len(recs)
+    E, V = ao.make_catalog(np.random.default_rng(0), nA, 4, 5)
+    eng = ag.Engine(R=1, A=nA, I=4, D=5, Do=4, P=2, mechanism=_lib.FIRST_PRICE, E=E, V=V, n_items=[4] * nA,
+                    alloc_kind=[_lib.ALLOC_ORACLE] * nA, bidder_kind=[_lib.BID_BANDIT] * nA, rounds_capacity=T,
+                    bidder_fit=[_lib.BFIT_PL_PPO] * nA)
+    eng.set_bidder_state(1.0, 0.02, initialised=0.0, policy_w=np.stack([z[f"a{a}_theta0"] for a in range(nA)])[None])
+    rows = np.zeros((T, 2, 5), np.float32)
+    meta = np.zeros((T, 2), np.uint32)
+    for t, (a, e, v, g, pr, u, won) in enumerate(recs):
+        rows[t, 0] = (e, v, g, pr, -u if won else 0.0)  # utility = value * click - price with click = 0
+        meta[t, 0] = (1 << 31) | (int(won) << 30) | int(a)
+    eng.bid_rows[0, :T].copy_(torch.from_numpy(rows))
+    eng.bid_meta[0, :T].copy_(torch.from_numpy(meta.view(np.int32)))
+    eng._check(eng.lib.agym_set_rounds_in_iteration(eng.handle, T))
+    info = eng.update_bidders().cpu().numpy()[0]
+    th = eng.bidder_w.cpu().numpy()[0, :, 4:16]
+    assert (eng.bidder_d.cpu().numpy()[0, :, 2] == 1.0).all()
+    for a in range(nA):
+        X = np.stack([z[f"a{a}_est"], z[f"a{a}_value"]], axis=1).astype(np.float32)
+        orc = po.fit_imitation(z[f"a{a}_theta0"], X, z[f"a{a}_gamma"])
+        assert info[a, 1, 3] == len(X) and info[a, 2, 3] == len(X)
+        assert info[a, 1, 1] == orc["n_epochs"], (info[a, 1], orc["n_epochs"])
+        np.testing.assert_allclose(info[a, 1, 2], orc["final_loss"], rtol=2e-3, atol=1e-7)
+        got, ref = po.forward(th[a], X), po.forward(z[f"a{a}_theta1"], X)
+        np.testing.assert_allclose(got["mu"].mean(), ref["mu"].mean(), atol=2e-3, err_msg=f"agent {a} mean mu")
+        np.testing.assert_allclose(got["mu"], ref["mu"], atol=1e-2, err_msg=f"agent {a} mu")
+        np.testing.assert_allclose(got["sigma"], ref["sigma"], atol=1e-2, err_msg=f"agent {a} sigma")
+    # re-running on an initialised policy skips initialise_policy (Bidder.py:381-382)
+    info2 = eng.update_bidders(max_epochs=50).cpu().numpy()[0]
+    assert (info2[:, 1, 1] == 0).all() and (info2[:, 2, 1] == 50).all()
+    eng.close()
+
+
+def test_policy_fit_fixed_budget_against_oracle():
+    """Every deterministic policy loss with a fixed epoch budget against the hand-differentiated oracle (whose gradients are
+    pinned to torch autograd in tests/test_oracle_golden.py)."""
+    _gpu()
+    import torch
+
+    import auction_gym_b200 as ag
+    from auction_gym_b200 import _lib
+    from oracle import policy_oracle as po
+
+    z = np.load(f"{GOLDEN_DIR}/bidfit_ppo.npz")
+    a = 1
+    X = np.stack([z[f"a{a}_est"], z[f"a{a}_value"]], axis=1).astype(np.float32)
+    g, pr, u, won = z[f"a{a}_gamma"], z[f"a{a}_prop"], z[f"a{a}_utility"], z[f"a{a}_won"]
+    kinds = [("REINFORCE", _lib.BFIT_PL_REINFORCE), ("REINFORCE_offpolicy", _lib.BFIT_PL_OFFPOLICY), ("TRPO", _lib.BFIT_PL_TRPO), ("PPO", _lib.BFIT_PL_PPO)]
+    nA, T = len(kinds), len(X)
+    E, V = ao.make_catalog(np.random.default_rng(0), nA, 4, 5)
+    eng = ag.Engine(R=1, A=nA, I=4, D=5, Do=4, P=4, mechanism=_lib.FIRST_PRICE, E=E, V=V, n_items=[4] * nA,
+                    alloc_kind=[_lib.ALLOC_ORACLE] * nA, bidder_kind=[_lib.BID_BANDIT] * nA, rounds_capacity=T,
+                    bidder_fit=[k for _, k in kinds])
+    th0 = z[f"a{a}_theta_imit"]
+    eng.set_bidder_state(1.0, 0.02, initialised=1.0, policy_w=np.broadcast_to(th0, (1, nA, 12)))
+    rows = np.zeros((T, 4, 5), np.float32)
+    meta = np.zeros((T, 4), np.uint32)
+    for s in range(nA):  # the same rows for every agent, one agent per slot
+        rows[:, s] = np.stack([X[:, 0], X[:, 1], g, pr, np.where(won, -u, 0.0)], axis=1)
+        meta[:, s] = (1 << 31) | (won.astype(np.uint32) << 30) | s
+    eng.bid_rows[0, :T].copy_(torch.from_numpy(rows))
+    eng.bid_meta[0, :T].copy_(torch.from_numpy(meta.view(np.int32)))
+    eng._check(eng.lib.agym_set_rounds_in_iteration(eng.handle, T))
+    info = eng.update_bidders(max_epochs=300).cpu().numpy()[0]
+    th = eng.bidder_w.cpu().numpy()[0, :, 4:16]
+    for s, (name, _) in enumerate(kinds):
+        orc = po.fit_policy_ppo(th0, X, g, pr, u, loss_name=name, max_epochs=300)
+        assert info[s, 2, 1] == 300 and info[s, 1, 1] == 0
+        np.testing.assert_allclose(th[s], orc["theta"], atol=2e-3, err_msg=name)
+        np.testing.assert_allclose(info[s, 2, 2], orc["final_loss"], rtol=2e-3, atol=1e-6, err_msg=name)
     eng.close()

@@ -115,9 +115,31 @@ def test_unbuilt_bidder_fits_fail_loudly(tmp_path):
     _need_gpu()
     import auction_gym_b200 as ag
 
-    path = _small_config(tmp_path, "FP_DR_TS", num_runs=2, num_iter=1, rounds_per_iter=200)
+    cfg = json.load(open(os.path.join(ROOT, "config", "FP_DM_Oracle.json")))
+    cfg["agents"][0]["bidder"] = {"type": "EmpiricalShadedBidder", "kwargs": {"gamma_sigma": 0.02, "init_gamma": 1.0}}
+    cfg.update(num_runs=2, num_iter=1, rounds_per_iter=200, output_dir=str(tmp_path) + "/")
+    path = str(tmp_path / "emp.json")
+    json.dump(cfg, open(path, "w"))
     with pytest.raises(ag.AgymError, match="not built yet"):
         ag.run_experiment(path)
+
+
+@pytest.mark.parametrize("cfg", ["FP_IPS_TS", "FP_DR_TS", "FP_DM_TS"])
+def test_policy_learning_configs_run_and_shade(tmp_path, cfg):
+    """config/FP_IPS_TS.json, FP_DR_TS.json, FP_DM_TS.json (BASELINE.json configs[3]): TS allocation + a learnt Gaussian
+    shading policy.  After the first update the policy drives the bids: gammas stay in [0, 1], every metric stays finite,
+    and the bidders no longer bid their full value."""
+    _need_gpu()
+    import auction_gym_b200 as ag
+
+    path = _small_config(tmp_path, cfg, num_runs=4, num_iter=3, rounds_per_iter=2000)
+    result = ag.run_experiment(path)
+    m = result["metrics"]  # [R, N, A, 10]
+    assert np.isfinite(m[..., :7]).all() and np.isfinite(m[..., 9]).all()
+    gamma = m[..., 9].mean(axis=(0, 2))
+    assert abs(gamma[0] - 1.0) < 0.01, gamma               # iteration 0: gamma ~ N(1, 0.02)
+    assert 0.0 <= gamma[1] <= 1.0 and 0.0 <= gamma[2] <= 1.0, gamma
+    assert gamma[2] < 0.999, gamma                           # a fitted policy samples below 1 and is clipped at 1
 
 
 def test_first_price_value_learning_config_learns_to_shade(tmp_path):
