@@ -196,3 +196,65 @@ def test_policy_fit_fixed_budget_against_oracle():
         np.testing.assert_allclose(th[s], orc["theta"], atol=2e-3, err_msg=name)
         np.testing.assert_allclose(info[s, 2, 2], orc["final_loss"], rtol=2e-3, atol=1e-6, err_msg=name)
     eng.close()
+
+
+@pytest.mark.parametrize("kind_name", ["DR", "VL_POLICY"])
+def test_stochastic_policy_fits_against_oracle_with_the_same_noise(kind_name):
+    """Doubly Robust (Models.py:198-218) and ValueLearning 'policy' (Bidder.py:292-302) draw fresh rsample noise every epoch.
+    The kernel's noise is Philox keyed by (seed, run, iteration, epoch, row), restated in oracle/philox_oracle.py, so a
+    fixed budget of epochs can be compared value for value (the device uses __logf / __sincosf: ~1e-6 per draw)."""
+    _gpu()
+    import torch
+
+    import auction_gym_b200 as ag
+    from auction_gym_b200 import _lib
+    from oracle import philox_oracle as ph
+    from oracle import policy_oracle as po
+
+    z = np.load(f"{GOLDEN_DIR}/bidfit_ppo.npz")
+    zw = np.load(f"{GOLDEN_DIR}/bidfit_winrate.npz")
+    a = 2
+    n = 900
+    X = np.stack([z[f"a{a}_est"], z[f"a{a}_value"]], axis=1).astype(np.float32)[:n]
+    g, pr, u, won = (z[f"a{a}_{k}"][:n] for k in ("gamma", "prop", "utility", "won"))
+    dr = kind_name == "DR"
+    E, V = ao.make_catalog(np.random.default_rng(0), 2, 4, 5)
+    eng = ag.Engine(R=2, A=2, I=4, D=5, Do=4, P=2, mechanism=_lib.FIRST_PRICE, E=E, V=V, n_items=[4, 4],
+                    alloc_kind=[_lib.ALLOC_ORACLE] * 2, bidder_kind=[_lib.BID_BANDIT if dr else _lib.BID_POLICY] * 2, rounds_capacity=n,
+                    bidder_fit=[_lib.BFIT_DR if dr else _lib.BFIT_VL_POLICY] * 2, run_offset=5)
+    th0, w0 = z[f"a{a}_theta_imit"], zw["a4_w0"]
+    eng.set_bidder_state(1.0, 0.02, initialised=1.0, winrate_w=w0, policy_w=th0)
+    rows = np.zeros((2, n, 2, 5), np.float32)
+    meta = np.zeros((2, n, 2), np.uint32)
+    run, agent = 1, 1  # only (run 1, agent 1) has rows: exercises the run / agent indexing of the noise counters
+    rows[run, :, 0] = np.stack([X[:, 0], X[:, 1], g, pr, np.where(won, -u, 0.0)], axis=1)
+    meta[run, :, 0] = (1 << 31) | (won.astype(np.uint32) << 30) | agent
+    eng.bid_rows[:, :n].copy_(torch.from_numpy(rows))
+    eng.bid_meta[:, :n].copy_(torch.from_numpy(meta.view(np.int32)))
+    eng._check(eng.lib.agym_set_rounds_in_iteration(eng.handle, n))
+    seed, it, budget = 77, 3, 120
+    info = eng.update_bidders(seed=seed, iteration=it, max_epochs=budget).cpu().numpy()[run, agent]
+    th = eng.bidder_w.cpu().numpy()[run, agent, 4:16]
+    ww = eng.bidder_w.cpu().numpy()[run, agent, 0:4]
+    # oracle: win-rate fit with the bidder's scheduler settings, then the policy fit with the same noise
+    wr = fo.fit_winrate(X[:, 0], X[:, 1], g, won, w0, max_epochs=budget, **(dict(patience=256, factor=0.2, stop_after=1024) if dr else {}))
+    np.testing.assert_allclose(ww, wr["w"], atol=2e-4)
+    W = ao.winrate32(wr["w"], np.stack([X[:, 0], X[:, 1], g], axis=1))
+    uhat = (W * (X[:, 0] * X[:, 1] - X[:, 0] * X[:, 1] * g)).astype(np.float32)
+    key = ph.make_key(seed, 5 + run)
+    noise = lambda e: ph.normal_x(np.arange(n, dtype=np.uint32), np.uint32(e), np.uint32((6 << 16) | agent), np.uint32(it), key)  # noqa: E731
+    lp = np.maximum(pr.astype(np.float32), np.float32(1e-15))
+    if dr:
+        lg = lambda t, eps: po.policy_loss_grad(t, X, g, lp, u, "Doubly Robust", utility_estimates=uhat, winrate_w=wr["w"], eps=eps)  # noqa: E731
+        orc = po.run_fit(th0, lg, lr=7e-3, weight_decay=1e-4, max_epochs=budget, stop_after=512,
+                         plateau=dict(patience=100, factor=0.2, min_lr=1e-8, threshold=5e-3), noise=noise)
+    else:
+        lg = lambda t, eps: po.policy_loss_grad(t, X, None, None, None, "DM", winrate_w=wr["w"], eps=eps)  # noqa: E731
+        orc = po.run_fit(th0, lg, lr=2e-3, weight_decay=1e-6, max_epochs=budget, stop_after=256,
+                         plateau=dict(patience=100, factor=0.1, min_lr=1e-7), noise=noise)
+    assert info[2, 1] == orc["n_epochs"] == budget and info[2, 3] == n
+    np.testing.assert_allclose(th, orc["theta"], atol=3e-3, err_msg=kind_name)
+    np.testing.assert_allclose(info[2, 2], orc["final_loss"], rtol=5e-3, atol=1e-5, err_msg=kind_name)
+    # rows of the other (run, agent) pairs are empty: their state is untouched
+    assert np.array_equal(eng.bidder_w.cpu().numpy()[0, 0, 4:16], th0)
+    eng.close()

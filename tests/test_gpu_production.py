@@ -159,3 +159,28 @@ def test_statistical_parity_with_oracle(name, precision):
     for a in range(int(case["A"])):
         close(acc[:, a, ao.M_GROSS], ref_acc[:, a, ao.M_GROSS], f"welfare of agent {a}")
     eng.close()
+
+
+def test_device_philox_matches_restatement():
+    """The in-kernel Philox4x32-10 + Box-Muller against oracle/philox_oracle.py (itself pinned to Random123's known-answer
+    vectors): contexts of the staged K1 kernel, value for value."""
+    gu = _gpu()
+    from auction_gym_b200 import _lib
+    from oracle import philox_oracle as ph
+
+    case, *_ = load_golden("rounds_sp_oracle")
+    R, T, seed, it = 3, 64, 0x1234567890ABCDEF, 5
+    eng = gu.engine_from_case(case, R=R, precision=_lib.FP32, run_offset=7)
+    b = eng.staged_round(seed, it, T, accumulate=False)
+    ctx = b["ctx"].cpu().numpy().reshape(R, T, eng.D)
+    for r in range(R):
+        key = ph.make_key(seed, 7 + r)
+        t = np.arange(T, dtype=np.uint32)
+        w0 = ph.philox4x32_10(t, np.uint32(it), np.uint32(0), np.uint32(0), key)   # purpose 0 (context), block 0: components 0..3
+        w1 = ph.philox4x32_10(t, np.uint32(it), np.uint32(0), np.uint32(1), key)   # block 1: component 4
+        n0, n1 = ph.box_muller(w0[0], w0[1])
+        n2, n3 = ph.box_muller(w0[2], w0[3])
+        n4, _ = ph.box_muller(w1[0], w1[1])
+        want = np.stack([n0, n1, n2, n3, n4], axis=1)
+        np.testing.assert_allclose(ctx[r], want, rtol=2e-5, atol=2e-6)
+    eng.close()

@@ -126,3 +126,17 @@ def test_bare_name_modules_like_the_reference():
         sys.path.pop(0)
         for mod in ("Agent", "Auction", "AuctionAllocation", "Bidder", "BidderAllocation", "Impression", "Models", "main"):
             sys.modules.pop(mod, None)
+
+
+def test_philox_restatement_known_answers():
+    """Random123's published known-answer vectors for philox4x32-10 (kat_vectors): the numpy restatement of the engine's
+    counter-based generator (csrc/agym_common.cuh) reproduces them; the device side is compared with the restatement in
+    tests/test_gpu_production.py."""
+    from oracle import philox_oracle as ph
+
+    z, f = np.uint32(0), np.uint32(0xFFFFFFFF)
+    assert [int(x) for x in ph.philox4x32_10(z, z, z, z, (z, z))] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert [int(x) for x in ph.philox4x32_10(f, f, f, f, (f, f))] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    c = [np.uint32(v) for v in (0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344)]
+    k = (np.uint32(0xA4093822), np.uint32(0x299F31D0))
+    assert [int(x) for x in ph.philox4x32_10(*c, k)] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
