@@ -2,11 +2,11 @@
 # Runs the six shipped experiment configs end to end on one GPU and records wall time + a result summary.
 mkdir -p gpurun_out/configs
 for c in SP_Oracle SP_Truthful_TS FP_DM_Oracle FP_DM_TS FP_DR_TS FP_IPS_TS; do
-  s=$(date +%s.%N)
+  s=$(date +%s%N)
   python auction-gym_b200/src/main.py config/$c.json --output-dir gpurun_out/configs/$c > gpurun_out/configs/$c.log 2>&1
   rc=$?
-  e=$(date +%s.%N)
-  echo "$c rc=$rc wall=$(echo "$e - $s" | bc) s"
+  e=$(date +%s%N)
+  echo "$c rc=$rc wall=$(( (e - s) / 1000000 )) ms"
 done
 python - <<'PY'
 import glob, pandas as pd
