@@ -15,7 +15,7 @@ BIDDER_D = 4
 BIDDER_W = 16
 BID_ROW = 5
 FIT_ADAM_REF, FIT_ADAM_FAST = 0, 1
-(BFIT_NONE, BFIT_VL_SEARCH, BFIT_VL_POLICY, BFIT_PL_REINFORCE, BFIT_PL_OFFPOLICY, BFIT_PL_TRPO, BFIT_PL_PPO, BFIT_DR) = range(8)
+(BFIT_NONE, BFIT_VL_SEARCH, BFIT_VL_POLICY, BFIT_PL_REINFORCE, BFIT_PL_OFFPOLICY, BFIT_PL_TRPO, BFIT_PL_PPO, BFIT_DR, BFIT_EMPIRICAL) = range(9)
 ABI_VERSION = 1
 
 # enum mirrors (include/agym.h)

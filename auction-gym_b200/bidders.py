@@ -82,11 +82,13 @@ class _ShadedBidder(Bidder):
 
 
 class EmpiricalShadedBidder(_ShadedBidder):
-    """One global gamma ~ N(prev_gamma, sigma) clipped to [0, 1] (Bidder.py:38-58).  Its bucketised
-    update (Bidder.py:60-147) is not built yet (no shipped config uses it)."""
+    """One global gamma ~ N(prev_gamma, sigma) clipped to [0, 1] (Bidder.py:38-58).  Its update
+    (Bidder.py:60-125: bucketised search for the gamma with the best lower confidence bound) runs in agym_update_bidders."""
 
     kind = _lib.BID_GAUSS_CLIP
     needs_fit = True
+    fit_built = True
+    fit_kind = _lib.BFIT_EMPIRICAL
 
 
 class ValueLearningBidder(_ShadedBidder):

@@ -166,15 +166,17 @@ int agym_set_bidder_fits(agym_handle* h, const int32_t* fit_kind) {
   std::vector<int32_t> kinds(A);
   cudaError_t e = cudaMemcpy(kinds.data(), h->d_bidder_kind, A * sizeof(int), cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return check_cuda(h, e, "agym_set_bidder_fits");
-  h->any_winrate_fit = h->any_policy_fit = h->any_unassigned_bandit = false;
+  h->any_winrate_fit = h->any_policy_fit = h->any_unassigned_bandit = h->any_empirical_fit = false;
   for (int a = 0; a < A; ++a) {
     const int f = fit_kind[a], k = kinds[a];
-    if (f < AGYM_BFIT_NONE || f > AGYM_BFIT_DR) return set_error(h, AGYM_ERR_INVALID, "agym_set_bidder_fits: unknown fit kind");
+    if (f < AGYM_BFIT_NONE || f > AGYM_BFIT_EMPIRICAL) return set_error(h, AGYM_ERR_INVALID, "agym_set_bidder_fits: unknown fit kind");
     const bool ok = (f == AGYM_BFIT_NONE) || (f == AGYM_BFIT_VL_SEARCH && k == AGYM_BID_SEARCH) || (f == AGYM_BFIT_VL_POLICY && k == AGYM_BID_POLICY) ||
-                    (f >= AGYM_BFIT_PL_REINFORCE && k == AGYM_BID_BANDIT);
+                    (f >= AGYM_BFIT_PL_REINFORCE && f <= AGYM_BFIT_DR && k == AGYM_BID_BANDIT) ||
+                    (f == AGYM_BFIT_EMPIRICAL && k == AGYM_BID_GAUSS_CLIP);
     if (!ok) return set_error(h, AGYM_ERR_INVALID, "agym_set_bidder_fits: fit kind does not match the agent's bid kind");
     h->any_winrate_fit |= f == AGYM_BFIT_VL_SEARCH || f == AGYM_BFIT_VL_POLICY || f == AGYM_BFIT_DR;
-    h->any_policy_fit |= f >= AGYM_BFIT_VL_POLICY;
+    h->any_policy_fit |= f >= AGYM_BFIT_VL_POLICY && f <= AGYM_BFIT_DR;
+    h->any_empirical_fit |= f == AGYM_BFIT_EMPIRICAL;
     h->any_unassigned_bandit |= (k == AGYM_BID_BANDIT || k == AGYM_BID_POLICY || k == AGYM_BID_SEARCH) && f == AGYM_BFIT_NONE;
   }
   e = cudaMemcpy(h->d_bidder_fit, fit_kind, A * sizeof(int), cudaMemcpyHostToDevice);
@@ -248,7 +250,7 @@ int agym_update_bidders(agym_handle* h, uint64_t seed, int32_t iter, int32_t max
   if (!h) return AGYM_ERR_INVALID;
   if (h->any_unassigned_bandit)
     return set_error(h, AGYM_ERR_STATE, "agym_update_bidders: an agent bids with a learnt model but has no fit kind (agym_set_bidder_fits)");
-  if (!h->any_winrate_fit && !h->any_policy_fit) return AGYM_OK;
+  if (!h->any_winrate_fit && !h->any_policy_fit && !h->any_empirical_fit) return AGYM_OK;
   if (!h->bidder_d || !h->bidder_w) return set_error(h, AGYM_ERR_STATE, "agym_update_bidders: bidder state not bound");
   if (!h->bid_rows) return set_error(h, AGYM_ERR_STATE, "agym_update_bidders: bid log not bound (agym_bind_bid_log)");
   if (max_epochs < 0) return set_error(h, AGYM_ERR_INVALID, "agym_update_bidders: max_epochs < 0");

@@ -46,8 +46,8 @@ struct BidFitParams {
 };
 
 __device__ __forceinline__ bool fits_winrate(int k) { return k == AGYM_BFIT_VL_SEARCH || k == AGYM_BFIT_VL_POLICY || k == AGYM_BFIT_DR; }
-__device__ __forceinline__ bool fits_policy(int k) { return k >= AGYM_BFIT_VL_POLICY; }
-__device__ __forceinline__ bool needs_imitation(int k) { return k >= AGYM_BFIT_PL_REINFORCE; }
+__device__ __forceinline__ bool fits_policy(int k) { return k >= AGYM_BFIT_VL_POLICY && k <= AGYM_BFIT_DR; }
+__device__ __forceinline__ bool needs_imitation(int k) { return k >= AGYM_BFIT_PL_REINFORCE && k <= AGYM_BFIT_DR; }
 
 __global__ void __launch_bounds__(256) bidrows_bucket_kernel(const BidFitParams p) {
   extern __shared__ int sm_i[];
@@ -440,6 +440,79 @@ __global__ void __launch_bounds__(256) policy_fit_kernel(const BidFitParams p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// EmpiricalShadedBidder.update (Bidder.py:60-125): bucketise the logged gammas (bucket width 0.005 between the smallest
+// and the largest gamma), estimate mean utility and its standard error per bucket, move prev_gamma to the centre of the
+// bucket with the best lower confidence bound (mean - 1.96 stderr; the highest bucket among ties), clipped to [0, 1].
+// ------------------------------------------------------------------------------------------------
+constexpr int kEmpMaxBuckets = 2048;
+__global__ void __launch_bounds__(256) empirical_update_kernel(const BidFitParams p) {
+  constexpr int NT = 256;
+  __shared__ float cnt[kEmpMaxBuckets], sum[kEmpMaxBuckets], dev2[kEmpMaxBuckets];
+  __shared__ float redmin[NT / 32], redmax[NT / 32];
+  const int run = blockIdx.x / p.A, a = blockIdx.x % p.A;
+  if (p.fit_kind[a] != AGYM_BFIT_EMPIRICAL) return;
+  const int tid = threadIdx.x;
+  const int* __restrict__ aoff = p.aoff + (size_t)run * (p.A + 1);
+  const int row0 = aoff[a], n = aoff[a + 1] - row0;
+  float* info = p.info ? p.info + ((size_t)run * p.A + a) * 12 : nullptr;
+  if (n == 0) return;
+  const float4* __restrict__ crow = reinterpret_cast<const float4*>(p.crow + ((size_t)run * p.Tcap * p.P + row0) * kRowF);
+  float lo = INFINITY, hi = -INFINITY;
+  for (int j = tid; j < n; j += NT) { const float g = crow[2 * j].z; lo = fminf(lo, g); hi = fmaxf(hi, g); }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off)); }
+  if ((tid & 31) == 0) { redmin[tid >> 5] = lo; redmax[tid >> 5] = hi; }
+  __syncthreads();
+  for (int w = 0; w < NT / 32; ++w) { lo = fminf(lo, redmin[w]); hi = fmaxf(hi, redmax[w]); }
+  const double dlo = double(lo), dhi = double(hi);
+  int nb = int(floor((dhi - dlo) / 0.005)) + 1;           // num_buckets = int((max - min) // grid_delta) + 1  (Bidder.py:82)
+  if (nb > kEmpMaxBuckets) nb = kEmpMaxBuckets;
+  const int nbk = nb - 1;                                  // np.linspace(min, max, nb) has nb - 1 intervals
+  const double step = nbk > 0 ? (dhi - dlo) / double(nbk) : 0.0;
+  for (int b = tid; b < nbk; b += NT) { cnt[b] = 0.f; sum[b] = 0.f; dev2[b] = 0.f; }
+  __syncthreads();
+  auto bucket_of = [&](float g) -> int {                   // bucket_lo <= gamma < bucket_hi  (Bidder.py:92)
+    if (nbk <= 0) return -1;
+    int b = int((double(g) - dlo) / step);
+    if (b >= nbk) b = nbk - 1;
+    while (b > 0 && double(g) < dlo + step * b) --b;
+    while (b < nbk - 1 && double(g) >= dlo + step * (b + 1)) ++b;
+    const double e_lo = dlo + step * b, e_hi = (b + 1 == nbk) ? dhi : dlo + step * (b + 1);
+    return (double(g) >= e_lo && double(g) < e_hi) ? b : -1;
+  };
+  for (int j = tid; j < n; j += NT) {
+    const int b = bucket_of(crow[2 * j].z);
+    if (b >= 0) { atomicAdd(&cnt[b], 1.0f); atomicAdd(&sum[b], crow[2 * j + 1].x); }
+  }
+  __syncthreads();
+  for (int j = tid; j < n; j += NT) {  // second pass: squared deviations from the bucket mean (np.std, population)
+    const int b = bucket_of(crow[2 * j].z);
+    if (b >= 0) { const float d = crow[2 * j + 1].x - sum[b] / cnt[b]; atomicAdd(&dev2[b], d * d); }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int best = -1;
+    float best_lb = -INFINITY;
+    for (int b = 0; b < nbk; ++b) {
+      if (cnt[b] > 1.5f) {  // num_samples > 1  (Bidder.py:95)
+        const float mean = sum[b] / cnt[b], se = sqrtf(dev2[b] / cnt[b]) / sqrtf(cnt[b]);
+        const float lb = mean - 1.96f * se;
+        if (lb >= best_lb) { best_lb = lb; best = b; }      // reversed nanargmax: the highest bucket among ties (Bidder.py:119)
+      }
+    }
+
+    if (best >= 0) {
+      const double b_lo = dlo + step * best, b_hi = (best + 1 == nbk) ? dhi : dlo + step * (best + 1);
+      double g = (b_hi - b_lo) / 2.0 + b_lo;                // Bidder.py:90
+      g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g);
+      p.bidder_d[((size_t)run * p.A + a) * AGYM_BIDDER_D + 0] = g;  // self.prev_gamma = best_gamma
+    }
+    if (info) { info[0] = float(best); info[1] = float(nbk); info[2] = best_lb; info[3] = float(n); }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 size_t bidder_workspace_bytes(const agym_handle* h, int64_t Tcap) {
   const agym_shape& s = h->shape;
@@ -495,6 +568,10 @@ int launch_update_bidders(agym_handle* h, uint64_t seed, int iter, int max_epoch
     pp.stage = kStageMain;
     policy_fit_kernel<<<grid, 256, 0, s>>>(pp);
     if ((rc = check_cuda(h, cudaGetLastError(), "policy_fit_kernel"))) return rc;
+  }
+  if (h->any_empirical_fit) {
+    empirical_update_kernel<<<grid, 256, 0, s>>>(bp);
+    if ((rc = check_cuda(h, cudaGetLastError(), "empirical_update_kernel"))) return rc;
   }
   return AGYM_OK;
 }

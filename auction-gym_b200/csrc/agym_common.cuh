@@ -187,7 +187,7 @@ struct agym_handle {
   int* d_bidder_kind = nullptr;
   int* d_bidder_fit = nullptr;
   int bidder_fit_host[4096];
-  bool any_winrate_fit = false, any_policy_fit = false, any_unassigned_bandit = false;
+  bool any_winrate_fit = false, any_policy_fit = false, any_unassigned_bandit = false, any_empirical_fit = false;
   double* d_E64 = nullptr;
   double* d_V64 = nullptr;
   float* d_E32 = nullptr;

@@ -85,7 +85,8 @@ class Engine:
         self._check(self.lib.agym_bind_bidder_state(self.handle, _ptr(self.bidder_d), _ptr(self.bidder_w)))
         self.fit_ctx = self.fit_meta = self.workspace = None
         self.bid_rows = self.bid_meta = self.bidder_workspace = None
-        self.learning_bidders = bool(np.isin(self.bidder_kind, [_lib.BID_SEARCH, _lib.BID_BANDIT, _lib.BID_POLICY]).any())
+        self.learning_bidders = bool(np.isin(self.bidder_kind, [_lib.BID_SEARCH, _lib.BID_BANDIT, _lib.BID_POLICY]).any()) or \
+            (bidder_fit is not None and bool((np.asarray(bidder_fit) != _lib.BFIT_NONE).any()))
         self.rounds_capacity = 0
         if rounds_capacity:
             self.reserve_rounds(rounds_capacity)

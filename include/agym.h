@@ -195,7 +195,8 @@ enum agym_bidder_fit {
   AGYM_BFIT_PL_OFFPOLICY = 4,
   AGYM_BFIT_PL_TRPO = 5,
   AGYM_BFIT_PL_PPO = 6,
-  AGYM_BFIT_DR = 7             /* DoublyRobustBidder                                               Bidder.py:477-615 */
+  AGYM_BFIT_DR = 7,            /* DoublyRobustBidder                                               Bidder.py:477-615 */
+  AGYM_BFIT_EMPIRICAL = 8      /* EmpiricalShadedBidder: bucketised search for prev_gamma          Bidder.py:60-125  */
 };
 int agym_set_bidder_fits(agym_handle* h, const int32_t* fit_kind /* [A], host */);
 /* Agent.update -> bidder.update for every (run, agent) whose bidder learns: win-rate fit, initialise_policy on the

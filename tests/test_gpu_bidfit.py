@@ -258,3 +258,41 @@ def test_stochastic_policy_fits_against_oracle_with_the_same_noise(kind_name):
     # rows of the other (run, agent) pairs are empty: their state is untouched
     assert np.array_equal(eng.bidder_w.cpu().numpy()[0, 0, 4:16], th0)
     eng.close()
+
+
+def test_empirical_shaded_bidder_update_matches_reference():
+    """EmpiricalShadedBidder.update (Bidder.py:60-125) on rows the reference logged: prev_gamma moves to the same bucket
+    centre (the device log is float32, the reference's lists float64: equal up to float32 resolution of the bucket edges)."""
+    _gpu()
+    import torch
+
+    import auction_gym_b200 as ag
+    from auction_gym_b200 import _lib
+    from oracle.empirical_oracle import fit_empirical
+
+    z = np.load(f"{GOLDEN_DIR}/bidfit_empirical.npz")
+    nA = 4
+    n = max(len(z[f"a{a}_gamma"]) for a in range(nA))
+    E, V = ao.make_catalog(np.random.default_rng(0), nA, 4, 5)
+    eng = ag.Engine(R=1, A=nA, I=4, D=5, Do=4, P=4, mechanism=_lib.FIRST_PRICE, E=E, V=V, n_items=[4] * nA,
+                    alloc_kind=[_lib.ALLOC_ORACLE] * nA, bidder_kind=[_lib.BID_GAUSS_CLIP] * nA, rounds_capacity=n,
+                    bidder_fit=[_lib.BFIT_EMPIRICAL] * nA)
+    eng.set_bidder_state([0.8, 0.6, 0.95, 0.5], [0.1, 0.15, 0.05, 0.3])
+    rows = np.zeros((n, 4, 5), np.float32)
+    meta = np.zeros((n, 4), np.uint32)
+    for a in range(nA):  # agent a in slot a
+        k = len(z[f"a{a}_gamma"])
+        won, click = z[f"a{a}_won"], z[f"a{a}_outcome"].astype(bool)
+        rows[:k, a] = np.stack([np.full(k, 0.1), z[f"a{a}_value"], z[f"a{a}_gamma"], np.ones(k), z[f"a{a}_price"]], axis=1)
+        meta[:k, a] = (1 << 31) | (won.astype(np.uint32) << 30) | ((won & click).astype(np.uint32) << 29) | a
+    eng.bid_rows[0, :n].copy_(torch.from_numpy(rows))
+    eng.bid_meta[0, :n].copy_(torch.from_numpy(meta.view(np.int32)))
+    eng._check(eng.lib.agym_set_rounds_in_iteration(eng.handle, n))
+    info = eng.update_bidders().cpu().numpy()[0, :, 0]
+    prev = eng.bidder_d.cpu().numpy()[0, :, 0]
+    for a in range(nA):
+        g_ref = float(z[f"a{a}_best_gamma"])
+        g_orc, b_orc, nb = fit_empirical(z[f"a{a}_gamma"], z[f"a{a}_utility"])
+        assert g_orc == g_ref and info[a, 3] == len(z[f"a{a}_gamma"]) and info[a, 1] == nb
+        assert abs(prev[a] - g_ref) < 1e-6, (a, prev[a], g_ref, info[a])
+    eng.close()

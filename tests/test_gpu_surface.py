@@ -111,17 +111,35 @@ def test_learning_config_improves_over_iterations(tmp_path):
     assert np.isfinite(m[..., :7]).all()
 
 
-def test_unbuilt_bidder_fits_fail_loudly(tmp_path):
+def test_unbuilt_features_fail_loudly(tmp_path):
+    """Log retention across iterations (`memory`, Agent.py:127-128) is the one agent option not built: it must raise."""
+    _need_gpu()
+    import auction_gym_b200 as ag
+
+    cfg = json.load(open(os.path.join(ROOT, "config", "SP_Oracle.json")))
+    cfg["agents"][0]["memory"] = 500
+    cfg.update(num_runs=2, num_iter=1, rounds_per_iter=200, output_dir=str(tmp_path) + "/")
+    path = str(tmp_path / "mem.json")
+    json.dump(cfg, open(path, "w"))
+    with pytest.raises(NotImplementedError, match="memory"):
+        ag.run_experiment(path)
+
+
+def test_empirical_shaded_bidder_config_runs(tmp_path):
+    """EmpiricalShadedBidder (Bidder.py:38-153) end to end: gamma is clipped to [0, 1] and prev_gamma moves after updates."""
     _need_gpu()
     import auction_gym_b200 as ag
 
     cfg = json.load(open(os.path.join(ROOT, "config", "FP_DM_Oracle.json")))
-    cfg["agents"][0]["bidder"] = {"type": "EmpiricalShadedBidder", "kwargs": {"gamma_sigma": 0.02, "init_gamma": 1.0}}
-    cfg.update(num_runs=2, num_iter=1, rounds_per_iter=200, output_dir=str(tmp_path) + "/")
+    cfg["agents"][0]["bidder"] = {"type": "EmpiricalShadedBidder", "kwargs": {"gamma_sigma": 0.1, "init_gamma": 0.9}}
+    cfg.update(num_runs=4, num_iter=3, rounds_per_iter=3000, output_dir=str(tmp_path) + "/")
     path = str(tmp_path / "emp.json")
     json.dump(cfg, open(path, "w"))
-    with pytest.raises(ag.AgymError, match="not built yet"):
-        ag.run_experiment(path)
+    result = ag.run_experiment(path)
+    gamma = result["metrics"][..., 9]  # [R, N, A]
+    assert np.isfinite(result["metrics"][..., :7]).all() and (gamma >= 0).all() and (gamma <= 1).all()
+    assert abs(gamma[:, 0].mean() - 0.9) < 0.02              # clipped N(0.9, 0.1) has a mean slightly below 0.9
+    assert np.abs(gamma[:, 1:] - 0.9).mean() > 0.01          # prev_gamma moved away from its initial value
 
 
 @pytest.mark.parametrize("cfg", ["FP_IPS_TS", "FP_DR_TS", "FP_DM_TS"])

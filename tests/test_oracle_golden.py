@@ -95,3 +95,13 @@ def test_imitation_fit_matches_reference():
     r = po.fit_imitation(z[f"a{a}_theta0"], X, z[f"a{a}_gamma"])
     assert r["n_epochs"] == 16384
     np.testing.assert_allclose(r["theta"], z[f"a{a}_theta_imit"], atol=1e-5)
+
+
+def test_empirical_bidder_update_matches_reference():
+    from oracle.empirical_oracle import fit_empirical
+    from tests.conftest import GOLDEN_DIR
+
+    z = np.load(f"{GOLDEN_DIR}/bidfit_empirical.npz")
+    for a in range(4):
+        g, _, _ = fit_empirical(z[f"a{a}_gamma"], z[f"a{a}_utility"])
+        assert g == float(z[f"a{a}_best_gamma"])
