@@ -467,7 +467,12 @@ __global__ void __launch_bounds__(256) empirical_update_kernel(const BidFitParam
   __syncthreads();
   for (int w = 0; w < NT / 32; ++w) { lo = fminf(lo, redmin[w]); hi = fmaxf(hi, redmax[w]); }
   const double dlo = double(lo), dhi = double(hi);
-  int nb = int(floor((dhi - dlo) / 0.005)) + 1;           // num_buckets = int((max - min) // grid_delta) + 1  (Bidder.py:82)
+  // num_buckets = int((max - min) // grid_delta) + 1  (Bidder.py:82).  Python's // is the floor of the EXACT quotient
+  // (1.0 // 0.005 == 199 although 1.0 / 0.005 rounds to 200.0), so the rounded quotient is corrected with an fma remainder.
+  double qd = floor((dhi - dlo) / 0.005);
+  const double rem = fma(-qd, 0.005, dhi - dlo);
+  if (rem < 0.0) qd -= 1.0; else if (rem >= 0.005) qd += 1.0;
+  int nb = int(qd) + 1;
   if (nb > kEmpMaxBuckets) nb = kEmpMaxBuckets;
   const int nbk = nb - 1;                                  // np.linspace(min, max, nb) has nb - 1 intervals
   const double step = nbk > 0 ? (dhi - dlo) / double(nbk) : 0.0;
