@@ -145,6 +145,7 @@ class Engine:
         """Upload learnt state ``[R, A, I, K]`` (numpy or torch, host or device); sigma is refreshed."""
         if not self.any_learnt:
             return
+        m, q, m_prev = (np.array(v, dtype=np.float32) if isinstance(v, np.ndarray) else v for v in (m, q, m_prev))
         self.m.copy_(torch.as_tensor(m, dtype=torch.float32).reshape(self.m.shape), non_blocking=non_blocking)
         if q is not None:
             self.q.copy_(torch.as_tensor(q, dtype=torch.float32).reshape(self.q.shape), non_blocking=non_blocking)
