@@ -320,9 +320,17 @@ def main():
                 "ms": ms4, "algorithmic_bytes": by, "opportunities_per_s": R * T / ms4 * 1e3, "traffic": None,
                 "note": f"{R * T} opportunities, {by / 1e6:.0f} MB algorithmic; L2 flushed (512 MB fill) before every timed launch; outside the timed step"}
         del b, flush
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures of exactly this
+    # shape (profiles/r1_fit_rows_ncu_full.txt, profiles/r1_sim_kernel_k4_ncu_full.txt); null for any other shape
+    std_shape = R == WORKLOAD["runs_per_gpu"] and T == WORKLOAD["T"] and learnt
+    ncu_traffic = {"sim_kernel (fused K1-K5)": 87844096 + 61523712, "bucket_kernel + fit_kernel (K6)": 300628736 + 207562240,
+                   "k4_resolve+accumulate": 141547520 + 49876736} if std_shape else {}
+    for k, v in {**kernels, **aux}.items():
+        v["traffic"] = ncu_traffic.get(k)
     dominant = max(kernels.items(), key=lambda kv: kv[1]["ms"])
     roofline = {"kernel": dominant[0], "bound": "hbm", "achieved": dominant[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dominant[1]["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": dominant[1]["achieved_gbs"] / peak, "traffic": ncu_traffic.get(dominant[0]), "peak_source": peak_src,
+                "issue_slots_used": 0.61 if std_shape else None,
                 "note": "the dominant kernel is not HBM-bound (" + dominant[1]["bound"] + "); its algorithmic HBM bytes are tiny by design. "
                         "The HBM-bound kernel of the path is the staged resolution kernel: see roofline_kernels.k4_resolve"}
 
