@@ -78,3 +78,28 @@ def test_product_path_does_not_touch_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{f} imports oracle/"
                 assert "/root/reference" not in text, f"{f} reads the reference tree"
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/agym.h must be usable from C (no C++ / torch types): compile and run a C program against libagym.so."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(
+        "#include <stdio.h>\n#include \"agym.h\"\n"
+        "int main(void) {\n"
+        "  agym_shape s = {1, 2, 2, 5, 4, 2, AGYM_SECOND_PRICE, AGYM_FP32, 0, 0, 1.0};\n"
+        "  agym_handle* h = 0;\n"
+        "  int bad = agym_create(0, 0, &h);                 /* null shape -> AGYM_ERR_INVALID */\n"
+        "  s.P = 3; int bad2 = agym_create(&s, 0, &h);      /* P > A -> AGYM_ERR_INVALID */\n"
+        "  printf(\"%d %d %d %s\\n\", agym_abi_version(), bad, bad2, agym_last_error(0));\n"
+        "  return (agym_abi_version() == AGYM_ABI_VERSION && bad == AGYM_ERR_INVALID && bad2 == AGYM_ERR_INVALID) ? 0 : 1;\n}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "auction-gym_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lagym", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("1 -1 -1 agym_create")
