@@ -28,8 +28,9 @@ STOP_AFTER, STOP_WINDOW, STOP_TOL = 1024, 100, 1e-6   # BidderAllocation.py:53
 
 def bce_sum32(p, y):
     """torch.nn.BCELoss(reduction='sum'): log terms clamped at -100 (Models.py:25)."""
-    lp = np.maximum(np.log(p), f32(-100.0))
-    l1p = np.maximum(np.log(f32(1.0) - p), f32(-100.0))
+    with np.errstate(divide="ignore"):  # log(0) = -inf is the case the clamp exists for
+        lp = np.maximum(np.log(p), f32(-100.0))
+        l1p = np.maximum(np.log(f32(1.0) - p), f32(-100.0))
     return -(y * lp + (f32(1.0) - y) * l1p).astype(f32).sum(dtype=f32)
 
 

@@ -1,7 +1,7 @@
 """GPU: the less-travelled code paths -- other embedding sizes (generic DMAX = 32 kernels, K = 9 / 33 fit variants), ragged
 catalogs, many participants, mixed allocators and bidders in one auction, the dense and the sparse fit kernels on the same
 data, and the shared-memory overflow path of the fit (rows beyond the staged capacity) -- replayed against the oracle."""
-import os
+import zlib
 
 import numpy as np
 import pytest
@@ -50,7 +50,7 @@ def test_odd_shapes_replay_and_fit(name):
     from auction_gym_b200 import _lib
 
     kw = SHAPES[name]
-    case, rng = _case(hash(name) % 1000, **kw)
+    case, rng = _case(zlib.crc32(name.encode()) % 1000, **kw)  # a fixed seed per shape (str hashes change per process)
     T = 700
     nz = ao.draw_replay_inputs(rng, T, case["A"], case["P"], case["D"], case["I"], case["Do"], 0.8,
                                want_eps=True, want_gamma=True)
@@ -60,7 +60,10 @@ def test_odd_shapes_replay_and_fit(name):
     rep = parity.compare_rounds(got, rec, rec, rtol=parity.RTOL_F64, est_rtol=parity.RTOL_F32_EST, what=name)
     acc, rev = eng.metrics()
     if rep["near_tie_rounds"] == 0:
-        np.testing.assert_allclose(acc[0], m["acc"], rtol=2e-6, atol=1e-9)
+        # the signed accumulators (estimation error, regrets) are sums of up to T terms built on float32 CTR estimates that
+        # agree to 4e-7 each and can cancel to ~0, so the meaningful bound on them is absolute: T * 4e-7 * |value| ~ 1e-5
+        # (a 40-seed sweep of these shapes, tools/shape_sweep.py, saw at most 1.1e-7)
+        np.testing.assert_allclose(acc[0], m["acc"], rtol=2e-6, atol=1e-5)
         np.testing.assert_allclose(rev[0], m["revenue"], rtol=2e-6)
     # allocator fit of every learnt agent on the rows the round loop logged, fixed epoch budget
     info = eng.update_allocators(max_epochs=150).cpu().numpy()[0]
@@ -71,7 +74,8 @@ def test_odd_shapes_replay_and_fit(name):
     for a in range(case["A"]):
         if case["alloc_kind"][a] == ao.ALLOC_ORACLE:
             continue
-        t_idx, s_idx = np.nonzero((nz["parts"] == a) & (rec["won"] == 1) & ~(rec["item_margin"] < parity.TIE_MARGIN).any(axis=1)[:, None])
+        # only compared when no arg-max flipped anywhere, so the device logged exactly the oracle's won rows
+        t_idx, s_idx = np.nonzero((nz["parts"] == a) & (rec["won"] == 1))
         if rep["near_tie_rounds"] or len(t_idx) < 2 or checked >= 12:
             continue
         nI = int(case["n_items"][a])
