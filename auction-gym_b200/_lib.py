@@ -14,6 +14,7 @@ NUM_METRICS = 12
 BIDDER_D = 4
 BIDDER_W = 16
 BID_ROW = 5
+TERM_ROW = 8         # AGYM_TERM_ROW
 FIT_ADAM_REF, FIT_ADAM_FAST = 0, 1
 (BFIT_NONE, BFIT_VL_SEARCH, BFIT_VL_POLICY, BFIT_PL_REINFORCE, BFIT_PL_OFFPOLICY, BFIT_PL_TRPO, BFIT_PL_PPO, BFIT_DR, BFIT_EMPIRICAL) = range(9)
 ABI_VERSION = 1
@@ -71,6 +72,9 @@ SIGNATURES = {
     "agym_rounds_in_iteration": (C.c_int64, [_H]),
     "agym_set_rounds_in_iteration": (C.c_int, [_H, C.c_int64]),
     "agym_clear_iteration": (C.c_int, [_H, C.c_void_p]),
+    "agym_set_log_retention": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "agym_retained_capacity": (C.c_int64, [_H]),
+    "agym_retain_logs": (C.c_int, [_H, C.c_void_p]),
     "agym_update_allocators": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "agym_bind_bid_log": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64]),
     "agym_bidder_workspace_bytes": (C.c_size_t, [_H, C.c_int64]),

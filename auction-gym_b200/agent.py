@@ -98,8 +98,6 @@ class Agent:
             self._auction.engine.acc[:, self._index, [_lib.M_NET, _lib.M_GROSS]] = 0.0
 
     def clear_logs(self):  # Agent.py:124-129
-        if self.memory:
-            raise NotImplementedError("memory > 0 (log retention across iterations, Agent.py:127-128) is not built yet")
         if self._auction is not None:
             self._auction._clear_agent_logs(self._index)
         self.bidder.clear_logs(memory=self.memory)

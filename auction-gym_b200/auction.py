@@ -49,6 +49,7 @@ class Auction:
         self._cleared = set()
         self._log_chunks = []   # detailed log of run 0 for the current iteration (list of dicts of numpy arrays)
         self._log_cache = None
+        self._retained = {}     # agent index -> (records, gammas, propensities) kept by clear_logs (Agent(memory=...))
         for i, ag in enumerate(self.agents):
             ag._attach(self, i)
 
@@ -71,7 +72,8 @@ class Auction:
                      alloc_kind=[ag.allocator.kind for ag in self.agents], bidder_kind=[ag.bidder.kind for ag in self.agents],
                      embedding_var=float(self.embedding_var), precision=self.precision, device=self.device,
                      run_offset=self.run_offset, rounds_capacity=self._rounds_capacity,
-                     bidder_fit=[ag.bidder.fit_kind for ag in self.agents])
+                     bidder_fit=[ag.bidder.fit_kind for ag in self.agents],
+                     memory=[int(ag.memory or 0) for ag in self.agents])
         if eng.any_learnt:
             m = np.zeros((self.num_runs, A, I, Do + 1), np.float32)
             q = np.ones_like(m)
@@ -107,9 +109,8 @@ class Auction:
         if self.engine is None:
             self._build()
         if self._cleared:  # an iteration boundary was only partly crossed (some agents cleared their logs, not all)
-            if len(self._cleared) != len(self.agents):
-                raise NotImplementedError("clear_logs() must be called for every agent before the next round "
-                                          "(per-agent log retention is not supported)")
+            raise NotImplementedError("clear_logs() must be called for every agent before the next round (the batched "
+                                      "logs are rewound once, when the last agent has cleared)")
         self._models_updated = False
         out = self.engine.simulate(self.seed, self.iteration, int(T), _LOG_FIELDS if keep_logs else None)
         if keep_logs:
@@ -153,26 +154,42 @@ class Auction:
         return self._log_cache
 
     def _agent_logs(self, index):
+        kept = self._retained.get(index, ([], [], []))[0]
         cols = self._log_columns()
-        if cols is None or index in self._cleared:  # clear_logs() of this agent already ran (Agent.py:124-126)
-            return []
-        return materialise_logs(cols, index, self.D_ctx)
+        if cols is None or index in self._cleared:  # clear_logs() of this agent already ran (Agent.py:124-129)
+            return list(kept)
+        return list(kept) + materialise_logs(cols, index, self.D_ctx)
 
     def _agent_log_column(self, index, name):
+        kept = self._retained.get(index, ([], [], []))[1 if name == "gamma" else 2]
         cols = self._log_columns()
         if cols is None or index in self._cleared:
-            return []
-        return list(cols[name][cols["agent"] == index])
+            return list(kept)
+        return list(kept) + list(cols[name][cols["agent"] == index])
+
+    def _roll_host_logs(self, index):
+        """Host view of Agent.clear_logs / Bidder.clear_logs (Agent.py:124-129, Bidder.py:149-153): keep the last `memory`."""
+        mem = int(self.agents[index].memory or 0)
+        if mem and (self._log_chunks or index in self._retained):
+            self._retained[index] = (self._agent_logs(index)[-mem:], self._agent_log_column(index, "gamma")[-mem:],
+                                     self._agent_log_column(index, "propensity")[-mem:])
+        else:
+            self._retained.pop(index, None)
 
     def _clear_agent_logs(self, index):
         if self.engine is None:
             return
-        keep = [_lib.M_NET, _lib.M_GROSS]
-        cols = [c for c in range(_lib.NUM_METRICS) if c not in keep]
-        self.engine.acc[:, index, cols] = 0.0
+        self._roll_host_logs(index)
+        if not self.agents[index].memory:
+            keep = [_lib.M_NET, _lib.M_GROSS]
+            cols = [c for c in range(_lib.NUM_METRICS) if c not in keep]
+            self.engine.acc[:, index, cols] = 0.0
         self._cleared.add(index)
         if len(self._cleared) == len(self.agents):  # every agent crossed the iteration boundary
-            self.engine._check(self.engine.lib.agym_set_rounds_in_iteration(self.engine.handle, 0))
+            if self.engine.retention:  # the kept records' sums replace the log-derived accumulators of every agent
+                self.engine.retain_logs()
+            else:
+                self.engine._check(self.engine.lib.agym_set_rounds_in_iteration(self.engine.handle, 0))
             self._log_chunks, self._log_cache = [], None
             self._cleared = set()
             self.iteration += 1
@@ -181,6 +198,8 @@ class Auction:
         """Batched equivalent of main.py:151-155 for all agents: clear utilities, logs and revenue."""
         if self.engine is None:
             return
+        for index in range(len(self.agents)):
+            self._roll_host_logs(index)
         self.engine.clear_iteration()
         self._log_chunks, self._log_cache = [], None
         self._cleared = set()

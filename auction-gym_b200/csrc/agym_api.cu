@@ -34,6 +34,7 @@ SimParams make_params(const agym_handle* h) {
   p.acc = h->acc; p.revenue = h->revenue;
   p.fit_ctx = h->fit_ctx; p.fit_meta = h->fit_meta; p.Tcap = h->Tcap;
   p.bid_rows = h->bid_rows; p.bid_meta = h->bid_meta; p.bid_Tcap = h->bid_Tcap;
+  p.terms = h->terms; p.log_base = h->log_base;
   p.round0 = h->rounds_in_iter;
   p.run0 = 0; p.n_runs = s.R;
   return p;
@@ -126,6 +127,7 @@ int agym_destroy(agym_handle* h) {
   DeviceGuard g(h->device);
   cudaFree(h->d_n_items); cudaFree(h->d_alloc_kind); cudaFree(h->d_bidder_kind); cudaFree(h->d_bidder_fit);
   cudaFree(h->d_E64); cudaFree(h->d_V64); cudaFree(h->d_E32); cudaFree(h->d_V32);
+  cudaFree(h->d_memory); cudaFree(h->d_mem_off);
   cudaFree(h->d_adam_sz0); cudaFree(h->d_adam_bc2s); cudaFree(h->k4_scratch); cudaFree(h->d_adam_bc1); cudaFree(h->d_adam_bc2s2);
   delete h;
   return AGYM_OK;
@@ -227,6 +229,8 @@ int agym_bind_metrics(agym_handle* h, double* acc, double* revenue) {
 int agym_bind_fit_log(agym_handle* h, float* fit_ctx, uint32_t* fit_meta, int64_t Tcap) {
   if (!h) return AGYM_ERR_INVALID;
   if ((fit_ctx == nullptr) != (fit_meta == nullptr) || Tcap < 0) return set_error(h, AGYM_ERR_INVALID, "agym_bind_fit_log: bad arguments");
+  if (h->log_base > 0 && (!fit_ctx || Tcap <= h->log_base + h->rounds_in_iter))
+    return set_error(h, AGYM_ERR_INVALID, "agym_bind_fit_log: with log retention the log must hold the retained rows and the rounds recorded so far");
   h->fit_ctx = fit_ctx; h->fit_meta = fit_meta; h->Tcap = fit_ctx ? Tcap : 0;
   return AGYM_OK;
 }
@@ -234,6 +238,8 @@ int agym_bind_fit_log(agym_handle* h, float* fit_ctx, uint32_t* fit_meta, int64_
 int agym_bind_bid_log(agym_handle* h, float* bid_rows, uint32_t* bid_meta, int64_t Tcap) {
   if (!h) return AGYM_ERR_INVALID;
   if ((bid_rows == nullptr) != (bid_meta == nullptr) || Tcap < 0) return set_error(h, AGYM_ERR_INVALID, "agym_bind_bid_log: bad arguments");
+  if (h->log_base > 0 && (!bid_rows || Tcap <= h->log_base + h->rounds_in_iter))
+    return set_error(h, AGYM_ERR_INVALID, "agym_bind_bid_log: with log retention the log must hold the retained rows and the rounds recorded so far");
   h->bid_rows = bid_rows; h->bid_meta = bid_meta; h->bid_Tcap = bid_rows ? Tcap : 0;
   return AGYM_OK;
 }
@@ -270,7 +276,7 @@ int64_t agym_rounds_in_iteration(const agym_handle* h) { return h ? h->rounds_in
 
 int agym_set_rounds_in_iteration(agym_handle* h, int64_t n) {
   if (!h) return AGYM_ERR_INVALID;
-  if (n < 0 || (h->fit_ctx && n > h->Tcap) || (h->bid_rows && n > h->bid_Tcap)) return set_error(h, AGYM_ERR_INVALID, "agym_set_rounds_in_iteration: out of range");
+  if (n < 0 || (h->fit_ctx && h->log_base + n > h->Tcap) || (h->bid_rows && h->log_base + n > h->bid_Tcap)) return set_error(h, AGYM_ERR_INVALID, "agym_set_rounds_in_iteration: out of range");
   h->rounds_in_iter = n;
   return AGYM_OK;
 }
@@ -286,9 +292,9 @@ int agym_simulate_rounds(agym_handle* h, uint64_t seed, int32_t iter, int64_t T,
   int rc = ready_for_rounds(h, "agym_simulate_rounds");
   if (rc) return rc;
   if ((rc = check_bidders_supported(h))) return rc;
-  if (h->any_learnt && h->fit_ctx && h->rounds_in_iter + T > h->Tcap)
+  if (h->any_learnt && h->fit_ctx && h->log_base + h->rounds_in_iter + T > h->Tcap)
     return set_error(h, AGYM_ERR_INVALID, "agym_simulate_rounds: fit log capacity exceeded (call agym_clear_iteration or bind a larger log)");
-  if (h->bid_rows && h->rounds_in_iter + T > h->bid_Tcap)
+  if (h->bid_rows && h->log_base + h->rounds_in_iter + T > h->bid_Tcap)
     return set_error(h, AGYM_ERR_INVALID, "agym_simulate_rounds: bid log capacity exceeded");
   if (T == 0) return AGYM_OK;
   DeviceGuard g(h->device);
@@ -308,8 +314,8 @@ int agym_replay_rounds(agym_handle* h, int32_t run0, int32_t n_runs, int64_t T, 
   if (rc) return rc;
   if (h->any_shaded && !in->gamma_z && !(h->any_search && in->grid_u && in->grid_n > 0))
     return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: shaded bidders need gamma_z (and grid_u once a win-rate model is fitted)");
-  if (h->fit_ctx && h->rounds_in_iter + T > h->Tcap) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: fit log capacity exceeded");
-  if (h->bid_rows && h->rounds_in_iter + T > h->bid_Tcap) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: bid log capacity exceeded");
+  if (h->fit_ctx && h->log_base + h->rounds_in_iter + T > h->Tcap) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: fit log capacity exceeded");
+  if (h->bid_rows && h->log_base + h->rounds_in_iter + T > h->bid_Tcap) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: bid log capacity exceeded");
   if (h->any_search && !in->grid_u) {
     // the 128-point search grid is only needed once some win-rate model is initialised; the kernel reads it lazily
   }
@@ -330,7 +336,54 @@ int agym_clear_iteration(agym_handle* h, void* stream) {
   cudaError_t e = cudaMemsetAsync(h->acc, 0, (size_t)s.R * s.A * kNumMetrics * sizeof(double), (cudaStream_t)stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(h->revenue, 0, (size_t)s.R * sizeof(double), (cudaStream_t)stream);
   h->rounds_in_iter = 0;
+  if (e == cudaSuccess && h->log_base > 0) return clear_retained_rows(h, (cudaStream_t)stream);
   return check_cuda(h, e, "agym_clear_iteration");
+}
+
+int agym_set_log_retention(agym_handle* h, const int32_t* memory, double* terms) {
+  if (!h) return AGYM_ERR_INVALID;
+  DeviceGuard g(h->device);
+  const int A = h->shape.A;
+  int64_t total = 0;
+  std::vector<int32_t> off(A, 0);
+  if (memory)
+    for (int a = 0; a < A; ++a) {
+      if (memory[a] < 0) return set_error(h, AGYM_ERR_INVALID, "agym_set_log_retention: memory < 0");
+      off[a] = int32_t(total);
+      total += memory[a];
+    }
+  if (h->rounds_in_iter != 0 && total != h->log_base)  // the rows already recorded would shift
+    return set_error(h, AGYM_ERR_STATE, "agym_set_log_retention: sum(memory) can only change between iterations (rounds are recorded)");
+  if (total == 0) {  // retention off
+    h->log_base = 0; h->terms = nullptr;
+    return AGYM_OK;
+  }
+  if (!terms) return set_error(h, AGYM_ERR_INVALID, "agym_set_log_retention: terms buffer required");
+  if (!h->bid_rows || h->bid_Tcap <= total) return set_error(h, AGYM_ERR_STATE, "agym_set_log_retention: bid log not bound or not larger than sum(memory)");
+  if (h->any_learnt && (!h->fit_ctx || h->Tcap <= total)) return set_error(h, AGYM_ERR_STATE, "agym_set_log_retention: winner log not bound or not larger than sum(memory)");
+  if (total > 0x7fffffffLL / h->shape.P) return set_error(h, AGYM_ERR_INVALID, "agym_set_log_retention: sum(memory) too large");
+  if (!h->d_memory) {
+    if (cudaMalloc(&h->d_memory, A * sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_mem_off, A * sizeof(int)) != cudaSuccess)
+      return check_cuda(h, cudaGetLastError(), "agym_set_log_retention");
+  }
+  cudaError_t e = cudaMemcpy(h->d_memory, memory, A * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_mem_off, off.data(), A * sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return check_cuda(h, e, "agym_set_log_retention");
+  h->log_base = total;
+  h->terms = terms;
+  return AGYM_OK;
+}
+
+int64_t agym_retained_capacity(const agym_handle* h) { return h ? h->log_base : -1; }
+
+int agym_retain_logs(agym_handle* h, void* stream) {
+  if (!h) return AGYM_ERR_INVALID;
+  if (h->log_base <= 0) return set_error(h, AGYM_ERR_STATE, "agym_retain_logs: log retention not configured (agym_set_log_retention)");
+  if (!h->acc) return set_error(h, AGYM_ERR_STATE, "agym_retain_logs: metrics not bound");
+  DeviceGuard g(h->device);
+  const int rc = launch_retain_logs(h, (cudaStream_t)stream);
+  if (rc == AGYM_OK) h->rounds_in_iter = 0;
+  return rc;
 }
 
 int agym_update_allocators(agym_handle* h, int32_t fit_mode, int32_t max_epochs, float* fit_info, void* stream) {

@@ -527,8 +527,8 @@ size_t bidder_workspace_bytes(const agym_handle* h, int64_t Tcap) {
 
 int launch_update_bidders(agym_handle* h, uint64_t seed, int iter, int max_epochs, float* fit_info, cudaStream_t s) {
   const agym_shape& sh = h->shape;
-  const int64_t Tn = h->rounds_in_iter;
-  if (Tn <= 0) return AGYM_OK;
+  if (h->rounds_in_iter <= 0 && h->log_base <= 0) return AGYM_OK;
+  const int64_t Tn = h->log_base + h->rounds_in_iter;  // retained rows (if any) come first
   if (h->bws == nullptr || h->bws_bytes < bidder_workspace_bytes(h, h->bid_Tcap))
     return set_error(h, AGYM_ERR_STATE, "agym_update_bidders: workspace not bound or too small (agym_bidder_workspace_bytes)");
   BidFitParams bp{};

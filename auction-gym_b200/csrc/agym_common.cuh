@@ -56,6 +56,8 @@ struct SimParams {
   float* bid_rows;     // [R][bid_Tcap][P][AGYM_BID_ROW]
   uint32_t* bid_meta;  // [R][bid_Tcap][P]
   long long bid_Tcap;
+  double* terms;       // [R][bid_Tcap][P][AGYM_TERM_ROW] metric summands per record (log retention only)
+  long long log_base;  // rows reserved at the head of both logs for retained records
   long long round0;  // rounds already simulated in this iteration (append offset and RNG counter base)
   long long T;       // rounds in this launch
   int run0, n_runs;  // runs covered by this launch
@@ -217,6 +219,11 @@ struct agym_handle {
   size_t bws_bytes = 0;
   bool any_search = false, any_unbuilt_fit = false;
   int64_t rounds_in_iter = 0;
+  // log retention (Agent.memory)
+  int* d_memory = nullptr;   // [A]
+  int* d_mem_off = nullptr;  // [A] first retained row of each agent
+  double* terms = nullptr;   // borrowed
+  int64_t log_base = 0;      // sum(memory)
   int num_sms = 148;
   std::string err;
 };
@@ -229,6 +236,8 @@ SimParams make_params(const agym_handle* h);
 // kernels' host launchers (one per translation unit)
 int launch_simulate(agym_handle* h, const SimParams& p, const agym_replay_inputs* in, const agym_round_log* log, cudaStream_t s);
 int launch_refresh_sigma(agym_handle* h, cudaStream_t s);
+int launch_retain_logs(agym_handle* h, cudaStream_t s);
+int clear_retained_rows(agym_handle* h, cudaStream_t s);
 int launch_update_allocators(agym_handle* h, int fit_mode, int max_epochs, float* fit_info, cudaStream_t s);
 size_t fit_workspace_bytes(const agym_handle* h, int64_t Tcap);
 int launch_update_bidders(agym_handle* h, uint64_t seed, int iter, int max_epochs, float* fit_info, cudaStream_t s);

@@ -94,33 +94,47 @@ __global__ void __launch_bounds__(256, DT > 0 ? 3 : 1) sim_kernel(const SimParam
 
     if (active) {
       // ---- charge / set_price and metric sums (Agent.py:70-118) ----
+      const long long tl = ta + p.log_base;  // row in the winner / bid logs (retained records sit in front)
       if (lane < P) {
         const bool won = valid && lane == wslot;
         const Real tv = r_true * r_val;
         double* __restrict__ ac = p.acc + ((size_t)run * A + my_agent) * kNumMetrics;
+        const Real de = r_true - r_est;
+        const double t_alloc = double(r_bev - tv), t_estim = double(r_est * r_val - tv), t_sq = double(de * de);
+        double t_over = 0.0, t_under = 0.0, t_bias = 0.0;
         if (won) {
           const Real got = click ? r_val : Real(0);
+          t_over = double(price - second_p);
+          t_bias = double(r_est / r_true);
           atomicAdd(ac + AGYM_M_NET, double(got - price));
           atomicAdd(ac + AGYM_M_GROSS, double(got));
-          atomicAdd(ac + AGYM_M_OVERBID_REGRET, double(price - second_p));
-          atomicAdd(ac + AGYM_M_BIAS, double(r_est / r_true));
+          atomicAdd(ac + AGYM_M_OVERBID_REGRET, t_over);
+          atomicAdd(ac + AGYM_M_BIAS, t_bias);
           atomicAdd(ac + AGYM_M_NWON, 1.0);
         } else if (price < tv) {
-          atomicAdd(ac + AGYM_M_UNDERBID_REGRET, double(price - r_bid));
+          t_under = double(price - r_bid);
+          atomicAdd(ac + AGYM_M_UNDERBID_REGRET, t_under);
         }
-        atomicAdd(ac + AGYM_M_ALLOC_REGRET, double(r_bev - tv));
-        atomicAdd(ac + AGYM_M_ESTIM_REGRET, double(r_est * r_val - tv));
-        const Real de = r_true - r_est;
-        atomicAdd(ac + AGYM_M_SQERR, double(de * de));
+        atomicAdd(ac + AGYM_M_ALLOC_REGRET, t_alloc);
+        atomicAdd(ac + AGYM_M_ESTIM_REGRET, t_estim);
+        atomicAdd(ac + AGYM_M_SQERR, t_sq);
         atomicAdd(ac + AGYM_M_NPART, 1.0);
         atomicAdd(ac + AGYM_M_BEST_EV, double(r_bev));
         if (r_gamma == r_gamma) atomicAdd(ac + AGYM_M_GAMMA, double(r_gamma));
+        // per-record summands, kept so that retained records can be re-summed next iteration (Agent.py:124-129)
+        if (p.terms != nullptr && tl < p.bid_Tcap) {
+          double2* __restrict__ tr = reinterpret_cast<double2*>(p.terms + (((size_t)run * p.bid_Tcap + tl) * P + lane) * AGYM_TERM_ROW);
+          tr[0] = make_double2(t_alloc, t_estim);
+          tr[1] = make_double2(t_over, t_under);
+          tr[2] = make_double2(t_sq, t_bias);
+          tr[3] = make_double2(r_gamma == r_gamma ? double(r_gamma) : 0.0, double(r_bev));
+        }
       }
       if (lane == 0 && valid) atomicAdd(p.revenue + run, double(price));  // Auction.py:74
 
       // ---- winner record for the allocator fit (Agent.py:81-91: won rows only) ----
-      if (p.fit_ctx != nullptr && ta < p.Tcap) {
-        const size_t fi = (size_t)run * p.Tcap + ta;
+      if (p.fit_ctx != nullptr && tl < p.Tcap) {
+        const size_t fi = (size_t)run * p.Tcap + tl;
 #pragma unroll
         for (int k = 0; k < DMAX; ++k)
           if (k < Do && lane == (k % G)) p.fit_ctx[fi * Do + k] = float(ctx[k]);
@@ -128,12 +142,12 @@ __global__ void __launch_bounds__(256, DT > 0 ? 3 : 1) sim_kernel(const SimParam
       }
 
       // ---- bid records for the bidder fits (Agent.py:81-94: bidder.update sees every row) ----
-      if (p.bid_rows != nullptr && ta < p.bid_Tcap && lane < P) {
+      if (p.bid_rows != nullptr && tl < p.bid_Tcap && lane < P) {
         const bool won = valid && lane == wslot;
-        const size_t bi = ((size_t)run * p.bid_Tcap + ta) * P + lane;
+        const size_t bi = ((size_t)run * p.bid_Tcap + tl) * P + lane;
         float* __restrict__ row = p.bid_rows + bi * AGYM_BID_ROW;
         row[0] = float(r_est); row[1] = float(r_val); row[2] = float(r_gamma); row[3] = float(r_prop); row[4] = float(price);
-        p.bid_meta[bi] = kBidValid | (won ? kBidWon : 0u) | ((won && click) ? kBidClick : 0u) | uint32_t(my_agent);
+        p.bid_meta[bi] = kBidValid | (won ? kBidWon : 0u) | ((won && click) ? kBidClick : 0u) | (uint32_t(r_item) << 12) | uint32_t(my_agent);
       }
 
       // ---- detailed log (Impression.py:4-31) ----

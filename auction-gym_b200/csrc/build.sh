@@ -8,7 +8,7 @@ OUT="$HERE/../libagym.so"
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -cudart static -I$ROOT/include -I$HERE"
 mkdir -p "$HERE/obj"
 pids=()
-for f in agym_api agym_sim agym_staged agym_fit agym_bidfit; do
+for f in agym_api agym_sim agym_staged agym_fit agym_bidfit agym_retain; do
   $NVCC $FLAGS ${AGYM_PTXAS_V:+-Xptxas -v} -c "$HERE/$f.cu" -o "$HERE/obj/$f.o" &
   pids+=($!)
 done

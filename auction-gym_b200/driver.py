@@ -138,8 +138,6 @@ def iteration_block(auction):
 
 def simulation_run(auction, num_iter, rounds_per_iter, verbose=False):
     """main.py:112-155 for every resident run at once.  Returns metrics [R, N, A, 10] and revenue [R, N]."""
-    if any(agent.memory for agent in auction.agents):
-        raise NotImplementedError("memory > 0 (log retention across iterations, Agent.py:127-128) is not built yet")
     blocks, revs = [], []
     for i in range(num_iter):
         auction.simulate_rounds(rounds_per_iter)

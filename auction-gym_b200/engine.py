@@ -35,7 +35,7 @@ class Engine:
     """
 
     def __init__(self, *, R, A, I, D, Do, P, mechanism, E, V, n_items, alloc_kind, bidder_kind, embedding_var=1.0,
-                 precision=_lib.FP32, device=0, run_offset=0, rounds_capacity=0, bidder_fit=None):
+                 precision=_lib.FP32, device=0, run_offset=0, rounds_capacity=0, bidder_fit=None, memory=None):
         if not torch.cuda.is_available():
             raise AgymError("CUDA device required: the AuctionGym B200 engine has no CPU fallback")
         self.lib = _lib.load()
@@ -87,6 +87,12 @@ class Engine:
         self.bid_rows = self.bid_meta = self.bidder_workspace = None
         self.learning_bidders = bool(np.isin(self.bidder_kind, [_lib.BID_SEARCH, _lib.BID_BANDIT, _lib.BID_POLICY]).any()) or \
             (bidder_fit is not None and bool((np.asarray(bidder_fit) != _lib.BFIT_NONE).any()))
+        # log retention across iterations (Agent(memory=...), Agent.py:124-129): rows reserved at the head of the logs
+        self.memory = np.zeros(self.A, np.int32) if memory is None else np.ascontiguousarray(memory, np.int32)
+        assert self.memory.shape == (self.A,) and (self.memory >= 0).all()
+        self.log_base = int(self.memory.sum())
+        self.retention = self.log_base > 0
+        self.terms = None
         self.rounds_capacity = 0
         if rounds_capacity:
             self.reserve_rounds(rounds_capacity)
@@ -112,32 +118,45 @@ class Engine:
             pass
 
     def reserve_rounds(self, T):
-        """Bind a winner log (fit_ctx / fit_meta) and fit workspace for up to T rounds per iteration."""
+        """Bind the winner log (fit_ctx / fit_meta), the bid log and the fit workspaces for up to T rounds per iteration
+        (plus the ``log_base`` rows that hold retained records when some agent has ``memory``)."""
         T = int(T)
         if T <= self.rounds_capacity:
             return
-        if not self.any_learnt and not self.learning_bidders:
+        need_bid = self.learning_bidders or self.retention
+        if not self.any_learnt and not need_bid:
             self.rounds_capacity = T
             return
-        if int(self.lib.agym_rounds_in_iteration(self.handle)) != 0:
-            raise AgymError("reserve_rounds: cannot grow the logs in the middle of an iteration")
-        dev = self.device
-        if self.learning_bidders:  # per-(round, slot) bid records for the bidder fits
-            self.bid_rows = torch.empty((self.R, T, self.P, _lib.BID_ROW), dtype=torch.float32, device=dev)
-            self.bid_meta = torch.zeros((self.R, T, self.P), dtype=torch.int32, device=dev)
-            self._check(self.lib.agym_bind_bid_log(self.handle, _ptr(self.bid_rows), _ptr(self.bid_meta), T))
-            nb = int(self.lib.agym_bidder_workspace_bytes(self.handle, T))
+        done = int(self.lib.agym_rounds_in_iteration(self.handle))
+        if done:  # growing in the middle of an iteration (simulate_opportunity() one round at a time): amortise
+            T = max(T, 2 * self.rounds_capacity)
+        dev, cap = self.device, T + self.log_base
+        filled = self.log_base + done  # retained rows + rounds recorded so far move to the new buffers
+
+        def grown(old, shape, dtype, zero):
+            new = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
+            if old is not None and filled:
+                new[:, :filled] = old[:, :filled]
+            return new
+
+        if need_bid:  # per-(round, slot) bid records for the bidder fits / retention
+            self.bid_rows = grown(self.bid_rows, (self.R, cap, self.P, _lib.BID_ROW), torch.float32, False)
+            self.bid_meta = grown(self.bid_meta, (self.R, cap, self.P), torch.int32, True)
+            self._check(self.lib.agym_bind_bid_log(self.handle, _ptr(self.bid_rows), _ptr(self.bid_meta), cap))
+        if self.learning_bidders:
+            nb = int(self.lib.agym_bidder_workspace_bytes(self.handle, cap))
             self.bidder_workspace = torch.empty((nb,), dtype=torch.uint8, device=dev)
             self._check(self.lib.agym_bind_bidder_workspace(self.handle, _ptr(self.bidder_workspace), nb))
-        if not self.any_learnt:
-            self.rounds_capacity = T
-            return
-        self.fit_ctx = torch.empty((self.R, T, max(self.Do, 1)), dtype=torch.float32, device=dev)
-        self.fit_meta = torch.zeros((self.R, T), dtype=torch.int32, device=dev)
-        self._check(self.lib.agym_bind_fit_log(self.handle, _ptr(self.fit_ctx), _ptr(self.fit_meta), T))
-        nbytes = int(self.lib.agym_workspace_bytes(self.handle, T))
-        self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-        self._check(self.lib.agym_bind_workspace(self.handle, _ptr(self.workspace), nbytes))
+        if self.any_learnt:
+            self.fit_ctx = grown(self.fit_ctx, (self.R, cap, max(self.Do, 1)), torch.float32, False)
+            self.fit_meta = grown(self.fit_meta, (self.R, cap), torch.int32, True)
+            self._check(self.lib.agym_bind_fit_log(self.handle, _ptr(self.fit_ctx), _ptr(self.fit_meta), cap))
+            nbytes = int(self.lib.agym_workspace_bytes(self.handle, cap))
+            self.workspace = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            self._check(self.lib.agym_bind_workspace(self.handle, _ptr(self.workspace), nbytes))
+        if self.retention:
+            self.terms = grown(self.terms, (self.R, cap, self.P, _lib.TERM_ROW), torch.float64, False)
+            self._check(self.lib.agym_set_log_retention(self.handle, self.memory.ctypes.data, _ptr(self.terms)))
         self.rounds_capacity = T
 
     # ------------------------------------------------------------------ state
@@ -229,7 +248,21 @@ class Engine:
 
     def clear_iteration(self):
         """Agent.clear_utility / clear_logs + Auction.clear_revenue for every run (Agent.py:120-129, Auction.py:76)."""
-        self._check(self.lib.agym_clear_iteration(self.handle, self._stream()))
+        if self.retention:
+            self.acc[:, :, [_lib.M_NET, _lib.M_GROSS]] = 0.0
+            self.revenue.zero_()
+            self.retain_logs()
+        else:
+            self._check(self.lib.agym_clear_iteration(self.handle, self._stream()))
+
+    def retain_logs(self):
+        """Agent.clear_logs for every agent with ``memory`` (Agent.py:124-129): keep the last memory[a] records, rewind
+        the logs, restart the log-derived accumulators from the kept records.  Utilities and revenue are untouched."""
+        if not self.retention:
+            raise AgymError("retain_logs: no agent has memory > 0")
+        if self.rounds_capacity == 0:
+            self.reserve_rounds(1)
+        self._check(self.lib.agym_retain_logs(self.handle, self._stream()))
 
     @property
     def rounds_in_iteration(self):

@@ -160,12 +160,36 @@ int agym_simulate_rounds(agym_handle* h, uint64_t seed, int32_t iter, int64_t T,
 int agym_replay_rounds(agym_handle* h, int32_t run0, int32_t n_runs, int64_t T, const agym_replay_inputs* in,
                        const agym_round_log* log, void* stream);
 int64_t agym_rounds_in_iteration(const agym_handle* h);
-/* For hosts that write fit_ctx / fit_meta themselves (log retention across iterations, Agent.py:124-129;
- * tests): declare how many rounds of the bound winner log are filled. */
+/* For hosts that write fit_ctx / fit_meta themselves (tests): declare how many rounds of the bound logs are
+ * filled (not counting the retained rows at their head). */
 int agym_set_rounds_in_iteration(agym_handle* h, int64_t n);
 /* Agent.clear_utility / clear_logs + Auction.clear_revenue (Agent.py:120-129, Auction.py:76): zero the
- * accumulators and rewind the fit log. */
+ * accumulators and rewind the logs; with log retention configured, also drops every retained record
+ * (the reference's memory == 0 behaviour). */
 int agym_clear_iteration(agym_handle* h, void* stream);
+
+/* ---- log retention across iterations (Agent(memory=...), Agent.py:124-129; Bidder.clear_logs, Bidder.py:149-153,
+ * 327-333,433-439,617-623) ----
+ * memory [A] (host): how many of its most recent records agent a keeps when an iteration ends (0 = none).
+ * The records live in the bound logs themselves: the first B = sum(memory) rows of the winner log and of the
+ * bid log are reserved ("retained rows", agent-major, oldest first, slot 0 only), the round loop appends behind
+ * them, and agym_update_allocators / agym_update_bidders read retained + new rows in the reference's order.
+ * Needs the bid log (agym_bind_bid_log) with bid_Tcap > B, the winner log too when some allocator learns, and
+ * terms [R][bid_Tcap][P][AGYM_TERM_ROW] double (device): the per-record summands of the metric getters
+ * (Agent.py:96-118, main.py:142-148) {allocation regret, estimation regret, overbid, underbid, squared CTR error,
+ * est/true on won rows, gamma, best expected value}, written by the round loop.
+ * The caller hands over bid_meta / fit_meta with their first B rows zeroed (no retained records yet), or holding
+ * records retained earlier (when it moves the logs to larger buffers: rebind the logs, then call this again with the
+ * new terms buffer).  memory == NULL switches retention off.  sum(memory) may only change between iterations. */
+#define AGYM_TERM_ROW 8
+int agym_set_log_retention(agym_handle* h, const int32_t* memory, double* terms);
+/* B = sum(memory): rows reserved at the head of the logs (0 when retention is off). */
+int64_t agym_retained_capacity(const agym_handle* h);
+/* Agent.clear_logs for every agent: keep each agent's last memory[a] records (retained + this iteration's, in
+ * time order), rewind the logs behind them, and set the ten log-derived accumulators of every (run, agent) to the
+ * sums over the kept records, which is what the reference's getters return from the shortened self.logs.
+ * Net / gross utility and revenue are NOT touched (Agent.clear_utility and Auction.clear_revenue are separate calls). */
+int agym_retain_logs(agym_handle* h, void* stream);
 
 /* ---- per-iteration model updates ---- */
 enum agym_fit_mode {
@@ -179,7 +203,7 @@ int agym_update_allocators(agym_handle* h, int32_t fit_mode, int32_t max_epochs,
 
 /* Per-(round, slot) bid records that feed the bidder fits (Agent.py:81-94: bidder.update sees ALL rows):
  * bid_rows [R][Tcap][P][AGYM_BID_ROW] float {estimated CTR, value, gamma, propensity, price},
- * bid_meta [R][Tcap][P] uint32 (bit 31 valid, bit 30 won, bit 29 click, bits 0..11 agent).
+ * bid_meta [R][Tcap][P] uint32 (bit 31 valid, bit 30 won, bit 29 click, bits 12..23 item, bits 0..11 agent).
  * Written by the round loop whenever a log is bound and some agent has a shaded bidder. */
 #define AGYM_BID_ROW 5
 int agym_bind_bid_log(agym_handle* h, float* bid_rows, uint32_t* bid_meta, int64_t Tcap);

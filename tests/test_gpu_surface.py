@@ -111,18 +111,31 @@ def test_learning_config_improves_over_iterations(tmp_path):
     assert np.isfinite(m[..., :7]).all()
 
 
-def test_unbuilt_features_fail_loudly(tmp_path):
-    """Log retention across iterations (`memory`, Agent.py:127-128) is the one agent option not built: it must raise."""
+def test_memory_config_retains_logs_across_iterations(tmp_path):
+    """`memory` in an agent's config (main.py:87, Agent.py:124-129): the getters sum over kept + new records, so the
+    allocation regret reported per iteration (a sum of non-negative terms) covers several iterations' rounds, and the
+    allocator is fitted on more rows."""
     _need_gpu()
     import auction_gym_b200 as ag
 
-    cfg = json.load(open(os.path.join(ROOT, "config", "SP_Oracle.json")))
-    cfg["agents"][0]["memory"] = 500
-    cfg.update(num_runs=2, num_iter=1, rounds_per_iter=200, output_dir=str(tmp_path) + "/")
-    path = str(tmp_path / "mem.json")
-    json.dump(cfg, open(path, "w"))
-    with pytest.raises(NotImplementedError, match="memory"):
-        ag.run_experiment(path)
+    res = {}
+    for mem in (0, 100000):
+        cfg = json.load(open(os.path.join(ROOT, "config", "SP_Truthful_TS.json")))
+        if mem:
+            for ac in cfg["agents"]:
+                ac["memory"] = mem
+        cfg.update(num_runs=4, num_iter=4, rounds_per_iter=1500, output_dir=str(tmp_path) + f"/m{mem}/")
+        path = str(tmp_path / f"mem{mem}.json")
+        json.dump(cfg, open(path, "w"))
+        res[mem] = ag.run_experiment(path)["metrics"]  # [R, N, A, 10]
+        assert np.isfinite(res[mem][..., :7]).all()
+    reg0, reg1 = res[0][..., 2].mean(axis=(0, 2)), res[100000][..., 2].mean(axis=(0, 2))  # allocation regret per iteration
+    assert abs(reg1[0] / reg0[0] - 1) < 0.2, (reg0, reg1)   # first iteration: nothing retained yet
+    assert reg1[-1] > 2.0 * reg0[-1], (reg0, reg1)          # fourth iteration: sums over four iterations' records
+    # utilities restart every iteration regardless of memory (Agent.py:120-122): same scale in both runs (the run with
+    # memory fits its allocators on more rows, so its welfare may be higher, not four times higher)
+    w0, w1 = res[0][..., 1].sum(axis=2).mean(axis=0), res[100000][..., 1].sum(axis=2).mean(axis=0)
+    assert np.all(w1 / w0 > 0.8) and np.all(w1 / w0 < 1.8), (w0, w1)
 
 
 def test_empirical_shaded_bidder_config_runs(tmp_path):

@@ -105,3 +105,31 @@ def test_empirical_bidder_update_matches_reference():
     for a in range(4):
         g, _, _ = fit_empirical(z[f"a{a}_gamma"], z[f"a{a}_utility"])
         assert g == float(z[f"a{a}_best_gamma"])
+
+
+def test_log_retention_matches_reference():
+    """Agent(memory=...) (Agent.py:124-129): what agent.logs holds at the end of each of four iterations, the getters'
+    values over those records and the rows Agent.update hands on, against the unmodified reference
+    (tests/golden/retention.npz, oracle/make_golden_retention.py)."""
+    from oracle import retention_oracle as ro
+    from tests import retention_util as ru
+
+    case, memory, inputs, ref = ru.load_retention()
+    out = ro.simulate_iterations(case, inputs, memory)
+    kept = np.zeros(len(memory), int)
+    for it, (o, r) in enumerate(zip(out, ref)):
+        rr = dict(r["rec"])
+        rr["winner"] = np.where(rr["won"].any(axis=1), rr["won"].argmax(axis=1), o["rec"]["winner"])
+        rep = parity.compare_rounds(o["rec"], rr, o["rec"], rtol=parity.RTOL_F64, est_rtol=parity.RTOL_F32_EST, what=f"it{it}")
+        assert rep["near_tie_rounds"] == 0
+        ru.check_logs_against_reference(o["logs"], r["agents"], case, parity.RTOL_F32_EST, what=f"it{it}")
+        parity.compare_metrics(o["acc"], o["revenue"], r["met"], rtol=2e-6, atol=1e-7, what=f"it{it}")
+        for a in range(len(memory)):
+            n_new = int((inputs[it]["parts"] == a).sum())
+            assert len(o["logs"][a]["won"]) == kept[a] + n_new  # kept records + this iteration's
+            kept[a] = min(kept[a] + n_new, memory[a])
+            assert kept[a] == int(r["agents"][a]["kept"])
+            g = r["agents"][a]["mean_gamma"]
+            if not np.isnan(g):
+                np.testing.assert_allclose(o["acc"][a, ao.M_GAMMA] / o["acc"][a, ao.M_NPART], g, rtol=1e-9)
+    assert kept.tolist() == [50, 300, 0, 130, 30]
