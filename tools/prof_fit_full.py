@@ -9,7 +9,7 @@ import auction_gym_b200 as ag  # noqa: E402
 from auction_gym_b200 import _lib  # noqa: E402
 from oracle import auction_oracle as ao  # noqa: E402
 
-R, T, A, I, D, Do, P = 512, 10000, 64, 64, 5, 4, 2
+R, T, A, I, D, Do, P = (int(sys.argv[1]) if len(sys.argv) > 1 else 512), 10000, 64, 64, 5, 4, 2
 E, V = ao.make_catalog(np.random.default_rng(0), A, I, D)
 eng = ag.Engine(R=R, A=A, I=I, D=D, Do=Do, P=P, mechanism=0, E=E, V=V, n_items=[I] * A, alloc_kind=[1] * A, bidder_kind=[0] * A,
                 precision=_lib.FP32, rounds_capacity=T)
