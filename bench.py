@@ -295,7 +295,7 @@ def main():
         kernels["bucket_kernel + fit_kernel (K6)"] = {"ms": k_ms["fit"], "share": k_ms["fit"] / (ms_total / args.steps),
                                                        "algorithmic_bytes": bytes_fit, "achieved_gbs": bytes_fit / k_ms["fit"] / 1e6,
                                                        "fits_per_s": R * A / k_ms["fit"] * 1e3, "rows_per_fit": rows_per_fit,
-                                                       "bound": "latency / issue: sequential Adam epochs on shared-memory-resident rows"}
+                                                       "bound": "instruction issue: ~8 000 sequential Adam epochs per fit on register / shared-memory resident state"}
     aux = {}
     if not args.no_aux:
         # staged resolution kernel K4(+K5) on the same opportunities: HBM-bound, 13P+10 = 36 B/opportunity
@@ -321,16 +321,18 @@ def main():
                 "note": f"{R * T} opportunities, {by / 1e6:.0f} MB algorithmic; L2 flushed (512 MB fill) before every timed launch; outside the timed step"}
         del b, flush
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures of exactly this
-    # shape (profiles/r1_fit_rows_ncu_full.txt, profiles/r1_sim_kernel_k4_ncu_full.txt); null for any other shape
+    # shape (profiles/r1_fit_warp_ncu_full.txt, profiles/r1_sim_kernel_k4_ncu_full.txt); null for any other shape
     std_shape = R == WORKLOAD["runs_per_gpu"] and T == WORKLOAD["T"] and learnt
-    ncu_traffic = {"sim_kernel (fused K1-K5)": 87844096 + 61523712, "bucket_kernel + fit_kernel (K6)": 300628736 + 207562240,
+    ncu_traffic = {"sim_kernel (fused K1-K5)": 87844096 + 61523712, "bucket_kernel + fit_kernel (K6)": 252042240 + 70073600,
                    "k4_resolve+accumulate": 141547520 + 49876736} if std_shape else {}
     for k, v in {**kernels, **aux}.items():
         v["traffic"] = ncu_traffic.get(k)
     dominant = max(kernels.items(), key=lambda kv: kv[1]["ms"])
     roofline = {"kernel": dominant[0], "bound": "hbm", "achieved": dominant[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dominant[1]["achieved_gbs"] / peak, "traffic": ncu_traffic.get(dominant[0]), "peak_source": peak_src,
-                "issue_slots_used": 0.61 if std_shape else None,
+                # what actually bounds it (same ncu capture): warp instructions issued per SM cycle against the 4 schedulers
+                "issue": {"achieved": 2.73, "peak": 4.0, "unit": "warp instructions / SM cycle", "frac": 0.68,
+                          "issue_slots_active": 0.72, "source": "profiles/r1_fit_warp_ncu_full.txt"} if std_shape else None,
                 "note": "the dominant kernel is not HBM-bound (" + dominant[1]["bound"] + "); its algorithmic HBM bytes are tiny by design. "
                         "The HBM-bound kernel of the path is the staged resolution kernel: see roofline_kernels.k4_resolve"}
 
