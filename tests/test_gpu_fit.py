@@ -172,3 +172,55 @@ def test_rounds_then_fit_end_to_end():
         np.testing.assert_allclose(q1[a], orc["q"], rtol=1e-4, err_msg=f"agent {a}")
         np.testing.assert_allclose(info[a, 2], orc["final_loss"], rtol=1e-5)
     eng.close()
+
+
+KERNEL_VARIANTS = {
+    "warp": {},                                                   # fit_warp_kernel (the default for this shape)
+    "warp_heavy4": {"AGYM_FIT_HEAVY": "4"},                       # ... with most items on the whole-warp path
+    "warp_overflow": {"AGYM_FIT_NCAP": "0.5"},                    # ... with half of the rows in the global overflow arrays
+    "cta64": {"AGYM_FIT_WARP": "0"},                              # fit_rows_kernel<5, ., 128>
+    "cta64_heavy4": {"AGYM_FIT_WARP": "0", "AGYM_FIT_HEAVY": "4"},
+    "cta_big": {"AGYM_FIT_WARP": "0", "AGYM_FIT_NT": "256"},      # fit_rows_kernel<5, false, 1024>: chunked segment sums
+    "dense": {"AGYM_FIT_WARP": "0", "AGYM_FIT_DENSE": "1"},       # fit_items_kernel: a warp per item
+}
+
+
+@pytest.mark.parametrize("variant", list(KERNEL_VARIANTS))
+@pytest.mark.parametrize("name", ["fit_ref_shape", "fit_64x64"])
+def test_every_fit_kernel_matches_the_oracle_on_a_fixed_budget(name, variant, monkeypatch):
+    """All K6 kernels implement the same state machine: with a fixed epoch budget (no chaotic stop) each of them must land
+    on the fit oracle's parameters, whichever one the launcher's shape heuristic would have picked."""
+    import torch
+
+    gu = _gpu()
+    for k, v in KERNEL_VARIANTS[variant].items():
+        monkeypatch.setenv(k, v)
+    z = np.load(f"{GOLDEN_DIR}/{name}.npz")
+    agents = [int(a) for a in z["fit_agents"]]
+    pre = [f"it1_a{a}_" for a in agents]
+    I, K = z[pre[0] + "m0"].shape
+    Do = K - 1
+    rows = []
+    for j, p in enumerate(pre):
+        X, items, y = z[p + "X"], z[p + "items"], z[p + "y"]
+        rows += [(r, j, X[r, :Do], items[r], y[r]) for r in range(len(y))]
+    rows.sort(key=lambda t: (t[0], t[1]))
+    T = len(rows)
+    eng = _engine_for_fits(gu, len(agents), I, Do, T)
+    eng.fit_ctx[0, :T].copy_(torch.from_numpy(np.stack([r[2] for r in rows]).astype(np.float32)))
+    meta = _pack_meta(np.array([r[1] for r in rows]), np.array([r[3] for r in rows]), np.array([r[4] for r in rows]) > 0)
+    eng.fit_meta[0, :T].copy_(torch.from_numpy(meta.view(np.int32)))
+    eng._check(eng.lib.agym_set_rounds_in_iteration(eng.handle, T))
+    eng.set_allocator_state(np.stack([z[p + "m0"] for p in pre])[None], np.stack([z[p + "q0"] for p in pre])[None],
+                            np.stack([z[p + "m_prev"] for p in pre])[None])
+    info = eng.update_allocators(max_epochs=300).cpu().numpy()[0]
+    m1, q1, mp = eng.m.cpu().numpy()[0], eng.q.cpu().numpy()[0], eng.m_prev.cpu().numpy()[0]
+    for j, p in enumerate(pre):
+        orc = fo.fit_allocator(z[p + "X"], z[p + "items"], z[p + "y"], z[p + "m0"], z[p + "q0"], z[p + "m_prev"], max_epochs=300)
+        what = f"{name} {variant} agent {agents[j]}"
+        assert info[j, 1] == 300 and info[j, 3] == len(z[p + "y"]), what
+        np.testing.assert_allclose(m1[j], orc["m"], atol=3e-4, err_msg=what)
+        np.testing.assert_allclose(q1[j], orc["q"], rtol=2e-4, err_msg=what)
+        np.testing.assert_allclose(info[j, 2], orc["final_loss"], rtol=2e-5, err_msg=what)
+        np.testing.assert_array_equal(mp[j], m1[j])
+    eng.close()
