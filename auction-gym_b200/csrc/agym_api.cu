@@ -281,17 +281,11 @@ int agym_set_rounds_in_iteration(agym_handle* h, int64_t n) {
   return AGYM_OK;
 }
 
-static int check_bidders_supported(agym_handle* h) {
-  // kinds >= SEARCH are served by their pre-fit Gaussian behaviour until the bidder fits (K7) land
-  return AGYM_OK;
-}
-
 int agym_simulate_rounds(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, const agym_round_log* log, void* stream) {
   if (!h) return AGYM_ERR_INVALID;
   if (T < 0) return set_error(h, AGYM_ERR_INVALID, "agym_simulate_rounds: T < 0");
   int rc = ready_for_rounds(h, "agym_simulate_rounds");
   if (rc) return rc;
-  if ((rc = check_bidders_supported(h))) return rc;
   if (h->any_learnt && h->fit_ctx && h->log_base + h->rounds_in_iter + T > h->Tcap)
     return set_error(h, AGYM_ERR_INVALID, "agym_simulate_rounds: fit log capacity exceeded (call agym_clear_iteration or bind a larger log)");
   if (h->bid_rows && h->log_base + h->rounds_in_iter + T > h->bid_Tcap)
@@ -316,9 +310,7 @@ int agym_replay_rounds(agym_handle* h, int32_t run0, int32_t n_runs, int64_t T, 
     return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: shaded bidders need gamma_z (and grid_u once a win-rate model is fitted)");
   if (h->fit_ctx && h->log_base + h->rounds_in_iter + T > h->Tcap) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: fit log capacity exceeded");
   if (h->bid_rows && h->log_base + h->rounds_in_iter + T > h->bid_Tcap) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: bid log capacity exceeded");
-  if (h->any_search && !in->grid_u) {
-    // the 128-point search grid is only needed once some win-rate model is initialised; the kernel reads it lazily
-  }
+  // (the 128-point search grid grid_u is only read once some win-rate model is initialised)
   if (T == 0) return AGYM_OK;
   DeviceGuard g(h->device);
   SimParams p = make_params(h);
