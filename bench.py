@@ -349,6 +349,26 @@ def main():
                "round_loop_only": r["round_only_per_core"], "host_cores": os.cpu_count(),
                "ideal_all_cores": cpu_val * (os.cpu_count() or 1)}
 
+    shipped = None
+    if rank == 0 and world == 1 and not args.no_aux:
+        # BASELINE.json configs[1] through the reference-facing driver (parse_config -> Auction / Agent -> five CSV tables'
+        # worth of metrics): 3 runs x 20 iterations x 10 000 rounds, 6 agents x 12 items, 360 allocator fits.  Wall clock,
+        # everything included (engine construction, catalog upload, fits, per-iteration metric read-out); second of two runs.
+        import auction_gym_b200 as ag
+
+        cfg_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "config", "SP_Truthful_TS.json")
+        walls = []
+        for _ in range(2):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            res = ag.run_experiment(cfg_path, device=local_rank)
+            torch.cuda.synchronize(dev)
+            walls.append(time.perf_counter() - t0)
+        c = res["config"]
+        n_opp = int(c.get("num_runs", res["metrics"].shape[0])) * c["num_iter"] * c["rounds_per_iter"]
+        shipped = {"config": "config/SP_Truthful_TS.json", "opportunities": n_opp, "wall_s": walls[-1], "value": n_opp / walls[-1], "unit": UNIT,
+                   "reference_published": {"wall_s": 1201, "value": 500, "where": "BASELINE.md: python src/main.py config/SP_Truthful_TS.json on 8 host cores"}}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -356,7 +376,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": args.steps * (3 if learnt else 1),
                 "round_loop": {"value": R * T * world / k_ms["rounds"] * 1e3 if k_ms["rounds"] else None, "unit": UNIT, "ms": k_ms["rounds"]},
-                "roofline": roofline, "roofline_kernels": {**kernels, **aux}, "cpu_baseline": cpu, "clocks": clk}
+                "roofline": roofline, "roofline_kernels": {**kernels, **aux}, "cpu_baseline": cpu, "shipped_config": shipped, "clocks": clk}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
