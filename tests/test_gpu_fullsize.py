@@ -62,3 +62,53 @@ def test_bench_shape_invariants():
     assert np.array_equal(m1r[~used], m0[run].numpy()[~used]) and (q1r[~used] == 1).all()
     assert (np.abs(m1r[used] - m0[run].numpy()[used]).max(axis=1) > 0).all() and (q1r[used] > 1).any()
     eng.close()
+
+
+def test_two_independent_fit_kernels_agree_at_the_bench_shape(monkeypatch):
+    """The warp-per-fit kernel (default) and the CTA kernel are separate implementations of the same optimiser.  On the
+    bench shape with the reference's full epoch budget they must reach the same optimum: final losses within 5e-4 rel
+    (items whose rows are all non-clicks have no finite optimum -- their intercept drifts until the stop rule fires),
+    stop epochs within the +-2 % (+-25) spread of the reference's own trajectory, parameters
+    within the fit bar (|dm| <= 1e-2 on the items that have rows), and each of them bit-reproducibly."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import auction_gym_b200 as ag
+    from auction_gym_b200 import _lib
+    from oracle import auction_oracle as ao
+
+    R, T, A, I, D, Do, P = 8, 10000, 64, 64, 5, 4, 2
+    E, V = ao.make_catalog(np.random.default_rng(0), A, I, D)
+    m0 = torch.randn(R, A, I, Do + 1, generator=torch.Generator().manual_seed(5))
+    out = {}
+    for name, env in (("warp", None), ("warp_again", None), ("cta", "0")):
+        if env is None:
+            monkeypatch.delenv("AGYM_FIT_WARP", raising=False)
+        else:
+            monkeypatch.setenv("AGYM_FIT_WARP", env)
+        eng = ag.Engine(R=R, A=A, I=I, D=D, Do=Do, P=P, mechanism=_lib.SECOND_PRICE, E=E, V=V, n_items=[I] * A,
+                        alloc_kind=[_lib.ALLOC_TS] * A, bidder_kind=[_lib.BID_TRUTHFUL] * A, rounds_capacity=T)
+        eng.set_allocator_state(m0)
+        for it in range(2):  # second iteration: rows concentrated on few items per agent
+            eng.clear_iteration()
+            eng.simulate(3, it, T)
+            info = eng.update_allocators().cpu().numpy()
+            if it == 0:
+                first = (eng.m.cpu().numpy().copy(), info.copy())
+                if name == "cta":  # continue from the warp kernel's state so that the second iteration sees the same rows
+                    eng.set_allocator_state(out["warp"]["m1"], out["warp"]["q1"])
+                else:
+                    out.setdefault(name, {})["m1"], out[name]["q1"] = eng.m.cpu().numpy().copy(), eng.q.cpu().numpy().copy()
+        meta = eng.fit_meta.cpu().numpy().view(np.uint32)
+        out.setdefault(name, {}).update(first=first, m=eng.m.cpu().numpy(), q=eng.q.cpu().numpy(), info=info, meta=meta)
+        eng.close()
+    w, w2, c = out["warp"], out["warp_again"], out["cta"]
+    assert np.array_equal(w["m"], w2["m"]) and np.array_equal(w["q"], w2["q"]) and np.array_equal(w["info"], w2["info"], equal_nan=True)
+    for a_, b_ in ((w["first"], c["first"]), ((w["m"], w["info"]), (c["m"], c["info"]))):
+        (ma, ia), (mb, ib) = a_, b_
+        assert np.array_equal(ia[..., 3], ib[..., 3])                                    # same rows per fit
+        np.testing.assert_allclose(ia[..., 2], ib[..., 2], rtol=5e-4)                     # same optimum
+        assert (np.abs(ia[..., 0] - ib[..., 0]) <= np.maximum(25, 0.02 * ib[..., 0])).mean() > 0.97   # stop epochs
+        assert np.abs(ma - mb).max() <= 2e-2 and np.mean(np.abs(ma - mb) > 1e-2) < 1e-4
+    assert np.array_equal(w["meta"], c["meta"])  # the second iteration really saw the same rows
