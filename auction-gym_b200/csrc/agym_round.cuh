@@ -108,6 +108,8 @@ __device__ __forceinline__ SlotEval<Real> eval_slot(const SimParams& p, int run,
 
   Real bscore = A_::neg_inf(), btv = A_::neg_inf();
   int bi = INT_MAX;
+  uint4 ts_bits = make_uint4(0u, 0u, 0u, 0u);
+  float2 ts_pair = make_float2(0.f, 0.f);
   for (int i = lane; i < nI; i += G) {
     const Real* __restrict__ e = Ea + (size_t)i * (D + 1);
     Real z = 0;
@@ -123,7 +125,28 @@ __device__ __forceinline__ SlotEval<Real> eval_slot(const SimParams& p, int run,
     if (akind != AGYM_ALLOC_ORACLE) {
       const float* __restrict__ mi = ma + (size_t)i * K;
       float zl = 0.0f;
-      if (akind == AGYM_ALLOC_TS) {
+      if (akind == AGYM_ALLOC_TS && !kReplay) {
+        // Production mode samples in logit space: with independent eps_k ~ N(0, 1) on the weights (Models.py:31),
+        // sum_k (m_k + eps_k sigma_k) x_k  ~  N(m.x, sum_k (sigma_k x_k)^2) exactly, so ONE normal per item gives the
+        // reference's distribution of sampled CTRs with a fifth of the normals.  (Replay mode below keeps the
+        // weight-space form: there the host supplies eps_k and parity is value for value.)
+        const float* __restrict__ si = sa + (size_t)i * K;
+        float var = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DMAX + 1; ++k) {
+          if (k < K) {
+            const float x = k < Do ? float(ctx[k < DMAX ? k : 0]) : 1.0f;
+            zl = fmaf(mi[k], x, zl);
+            const float sx = si[k] * x;
+            var = fmaf(sx, sx, var);
+          }
+        }
+        // one Philox block serves four consecutive items of this lane, one Box-Muller pair two of them
+        const int t = (i - lane) / G;
+        if ((t & 3) == 0) ts_bits = philox4x32_10(rc.c0, rc.c1, (kPurposeTS << 16) | uint32_t(s), uint32_t(i), key);
+        if ((t & 1) == 0) ts_pair = (t & 2) ? box_muller(ts_bits.z, ts_bits.w) : box_muller(ts_bits.x, ts_bits.y);
+        zl = fmaf(sqrtf(var), (t & 1) ? ts_pair.y : ts_pair.x, zl);
+      } else if (akind == AGYM_ALLOC_TS) {
         const float* __restrict__ si = sa + (size_t)i * K;
 #pragma unroll
         for (int kb = 0; kb < (DMAX + 4) / 4; ++kb) {

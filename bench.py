@@ -289,8 +289,10 @@ def main():
         kernels["sim_kernel (fused K1-K5)"] = {"ms": k_ms["rounds"], "share": k_ms["rounds"] / (ms_total / args.steps),
                                                 "algorithmic_bytes": bytes_rounds, "achieved_gbs": bytes_rounds / k_ms["rounds"] / 1e6,
                                                 "opportunities_per_s": R * T / k_ms["rounds"] * 1e3,
-                                                "normals_per_s": (R * T * P * I * K / k_ms["rounds"] * 1e3) if learnt else 0.0,
-                                                "bound": "issue (Philox + Box-Muller + exp); HBM traffic is the 20 B/opportunity winner record"}
+                                                # production mode draws the Thompson noise in logit space: one normal per (participant, item)
+                                                "normals_per_s": (R * T * P * I / k_ms["rounds"] * 1e3) if learnt else 0.0,
+                                                "sigmoids_per_s": R * T * P * (2 * I + 1) / k_ms["rounds"] * 1e3,
+                                                "bound": "issue (exp, FMA, Philox + Box-Muller) and L1/L2 reads of the learnt state; HBM traffic is the 20 B/opportunity winner record"}
     if learnt and k_ms["fit"] > 0:
         kernels["bucket_kernel + fit_kernel (K6)"] = {"ms": k_ms["fit"], "share": k_ms["fit"] / (ms_total / args.steps),
                                                        "algorithmic_bytes": bytes_fit, "achieved_gbs": bytes_fit / k_ms["fit"] / 1e6,
