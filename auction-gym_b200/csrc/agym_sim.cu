@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(256, DT > 0 ? 3 : 1) sim_kernel(const SimParam
   const int iters = (p.chunk + ngroups - 1) / ngroups;
   const int D = DT > 0 ? DT : p.D, Do = DT > 0 ? DoT : p.Do, P = p.P, A = p.A;
   const PhiloxKey key = make_key(p.seed, uint32_t(p.run_offset + run));
+  const bool has_log = log.agent || log.item || log.est || log.value || log.bid || log.true_ctr || log.best_ev || log.price || log.second ||
+                       log.gamma || log.propensity || log.outcome || log.won || log.winner || log.ctx;
 
   for (int it = 0; it < iters; ++it) {
     const long long t_raw = tb + (long long)it * ngroups + group;
@@ -150,8 +152,8 @@ __global__ void __launch_bounds__(256, DT > 0 ? 3 : 1) sim_kernel(const SimParam
         p.bid_meta[bi] = kBidValid | (won ? kBidWon : 0u) | ((won && click) ? kBidClick : 0u) | (uint32_t(r_item) << 12) | uint32_t(my_agent);
       }
 
-      // ---- detailed log (Impression.py:4-31) ----
-      if (lane < P) {
+      // ---- detailed log (Impression.py:4-31); `has_log` spares the production launch the per-field null checks ----
+      if (has_log && lane < P) {
         const bool won = valid && lane == wslot;
         const size_t li = (size_t)ri * P + lane;
         if (log.agent) log.agent[li] = my_agent;
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(256, DT > 0 ? 3 : 1) sim_kernel(const SimParam
         if (log.outcome) log.outcome[li] = (won && click) ? 1 : 0;
         if (log.won) log.won[li] = won ? 1 : 0;
       }
-      if (lane == 0) {
+      if (has_log && lane == 0) {
         if (log.winner) log.winner[ri] = wslot;
         if (log.ctx) {
 #pragma unroll
