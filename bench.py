@@ -330,7 +330,7 @@ def main():
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures of exactly this
     # shape (profiles/r1_fit_warp_ncu_full.txt, profiles/r1_sim_kernel_logit_ts_ncu_full.txt, profiles/r1_sim_kernel_k4_ncu_full.txt); null for any other shape
     std_shape = R == WORKLOAD["runs_per_gpu"] and T == WORKLOAD["T"] and learnt
-    ncu_traffic = {"sim_kernel (fused K1-K5)": 88196352 + 64818688, "bucket_kernel + fit_kernel (K6)": 251330048 + 69806336,
+    ncu_traffic = {"sim_kernel (fused K1-K5)": 88196352 + 64818688, "bucket_kernel + fit_kernel (K6)": 250489600 + 71059200,
                    "k4_resolve+accumulate": 141547520 + 49876736} if std_shape else {}
     for k, v in {**kernels, **aux}.items():
         v["traffic"] = ncu_traffic.get(k)
@@ -338,8 +338,8 @@ def main():
     roofline = {"kernel": dominant[0], "bound": "hbm", "achieved": dominant[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dominant[1]["achieved_gbs"] / peak, "traffic": ncu_traffic.get(dominant[0]), "peak_source": peak_src,
                 # what actually bounds it (same ncu capture): warp instructions issued per SM cycle against the 4 schedulers
-                "issue": {"achieved": 2.78, "peak": 4.0, "unit": "warp instructions / SM cycle", "frac": 0.70,
-                          "issue_slots_active": 0.73, "warp_instructions_per_fit_epoch": 974, "source": "profiles/r1_fit_warp_ncu_full.txt"} if std_shape else None,
+                "issue": {"achieved": 2.73, "peak": 4.0, "unit": "warp instructions / SM cycle", "frac": 0.68,
+                          "issue_slots_active": 0.73, "warp_instructions_per_fit_epoch": 943, "source": "profiles/r1_fit_warp_ncu_full.txt"} if std_shape else None,
                 "note": "the dominant kernel is not HBM-bound (" + dominant[1]["bound"] + "); its algorithmic HBM bytes are tiny by design. "
                         "The HBM-bound kernel of the path is the staged resolution kernel: see roofline_kernels.k4_resolve"}
 
