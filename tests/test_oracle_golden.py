@@ -133,3 +133,32 @@ def test_log_retention_matches_reference():
             if not np.isnan(g):
                 np.testing.assert_allclose(o["acc"][a, ao.M_GAMMA] / o["acc"][a, ao.M_NPART], g, rtol=1e-9)
     assert kept.tolist() == [50, 300, 0, 130, 30]
+
+
+def test_log_retention_oracle_limits():
+    """Size-independent properties of Agent(memory=...): memory 0 is the plain per-iteration reset, a memory larger than
+    everything ever logged makes the log-derived accumulators cumulative, memory 1 keeps exactly the last record."""
+    from oracle import retention_oracle as ro
+    from tests import retention_util as ru
+
+    case, _, inputs, _ = ru.load_retention()
+    A = int(case["A"])
+    plain = [ao.simulate_rounds(case, nz["ctx"], nz["parts"], nz["u"], nz.get("ts_eps"), nz.get("gamma_z"))[1]["acc"] for nz in inputs]
+    none = ro.simulate_iterations(case, inputs, np.zeros(A, int))
+    keep_all = ro.simulate_iterations(case, inputs, np.full(A, 10**6))
+    one = ro.simulate_iterations(case, inputs, np.ones(A, int))
+    logged = [ao.M_ALLOC_REG, ao.M_ESTIM_REG, ao.M_OVERBID, ao.M_UNDERBID, ao.M_SQERR, ao.M_BIAS, ao.M_NPART, ao.M_NWON, ao.M_BEST_EV, ao.M_GAMMA]
+    cum = np.zeros_like(plain[0])
+    for it in range(len(inputs)):
+        np.testing.assert_allclose(none[it]["acc"], plain[it], rtol=1e-12, atol=1e-12)
+        cum += plain[it]
+        np.testing.assert_allclose(keep_all[it]["acc"][:, logged], cum[:, logged], rtol=1e-10, atol=1e-10)
+        for o in (none, keep_all, one):  # utilities always restart (Agent.py:120-122)
+            np.testing.assert_allclose(o[it]["acc"][:, [ao.M_NET, ao.M_GROSS]], plain[it][:, [ao.M_NET, ao.M_GROSS]], rtol=1e-12, atol=1e-12)
+        if it > 0:
+            extra = one[it]["acc"][:, ao.M_NPART] - plain[it][:, ao.M_NPART]
+            took_part_before = np.array([(np.concatenate([nz["parts"].ravel() for nz in inputs[:it]]) == a).any() for a in range(A)])
+            assert np.array_equal(extra, took_part_before.astype(float))
+            for a in range(A):  # ... and it is the most recent one
+                last = one[it - 1]["logs"][a]
+                assert one[it]["logs"][a]["best_ev"][0] == last["best_ev"][-1]
