@@ -8,6 +8,8 @@
 //   lowest-slot tie-break (AuctionAllocation.py:18-35) -> Bernoulli click (Auction.py:65) ->
 //   charge / set_price / revenue and every per-agent metric (Agent.py:70-118, main.py:131-148).
 // The same body serves production mode (in-kernel Philox noise) and replay mode (host-drawn noise).
+#include <cstdlib>
+
 #include "agym_round.cuh"
 
 namespace agym {
@@ -224,7 +226,13 @@ static int launch_g(agym_handle* h, const SimParams& p, const agym_replay_inputs
 
 template <typename Real, int DMAX>
 static int launch_d(agym_handle* h, const SimParams& p, const agym_replay_inputs* in, const agym_round_log* log, cudaStream_t s) {
+  // Lane-group width.  Everything outside the item loop (context, participants, resolution, click, accumulators: more than
+  // half of the instructions at 64 items) is issued once per warp instruction whatever G is, so narrow groups -- more
+  // opportunities per warp, more items per lane -- amortise it: B200, bench shape, G = 32 / 16 / 8 -> 10.6 / 7.7 / 7.2 ms
+  // (Oracle allocators 6.1 / 4.7 / 3.6 ms).  Small launches keep wide groups: they need the parallelism more.
   int G = h->max_items > 16 ? 32 : (h->max_items > 8 ? 16 : 8);
+  if ((long long)p.n_runs * p.T >= 65536) G = 8;
+  if (const char* env = getenv("AGYM_SIM_G")) { const int v = atoi(env); if (v == 8 || v == 16 || v == 32) G = v; }  // experiment knob
   while (G < p.P) G *= 2;
   if (DMAX / 4 > G) G = 32;
   switch (G) {

@@ -54,6 +54,32 @@ def test_replay_fp64_matches_oracle_and_reference(name):
     eng.close()
 
 
+@pytest.mark.parametrize("G", ["8", "16", "32"])
+@pytest.mark.parametrize("name", ["rounds_sp_ts_64x64", "rounds_sp_oracle_64x64", "rounds_fp_pA", "rounds_sp_ragged", "rounds_fp_search", "rounds_fp_bandit"])
+def test_replay_is_exact_for_every_lane_group_width(name, G, monkeypatch):
+    """The launcher picks the lane-group width from the catalog width and the launch size (8 lanes for large launches);
+    every width must reproduce the reference's discrete decisions -- forced here through the AGYM_SIM_G experiment knob."""
+    gu = _gpu()
+    from auction_gym_b200 import _lib
+
+    monkeypatch.setenv("AGYM_SIM_G", G)
+    case, inp, ref, met = load_golden(name)
+    eng = gu.engine_from_case(case, R=1, precision=_lib.FP64)
+    got = gu.log_to_numpy(gu.replay_case(eng, inp))
+    rec, m = ao.simulate_rounds(case, inp["ctx"], inp["parts"], inp["u"], inp.get("ts_eps"), inp.get("gamma_z"), inp.get("grid_u"))
+    learnt = bool((case["alloc_kind"] != ao.ALLOC_ORACLE).any())
+    net = bool(np.isin(case["bidder_kind"], [ao.BID_BANDIT, ao.BID_POLICY]).any())
+    gtol = dict(gamma_rtol=2e-6, prop_rtol=2e-4) if net else {}
+    est_rtol = parity.RTOL_F32_EST if (learnt or net) else parity.RTOL_F64
+    ref = dict(ref)
+    ref["winner"] = np.where(ref["won"].any(axis=1), ref["won"].argmax(axis=1), rec["winner"])
+    rep = parity.compare_rounds(got, ref, rec, rtol=parity.RTOL_F64, est_rtol=est_rtol, what=f"{name} G={G} cuda-vs-reference", **gtol)
+    assert rep["near_tie_rounds"] == 0
+    acc, rev = eng.metrics()
+    parity.compare_metrics(acc[0], rev[0], met, rtol=2e-6 if (learnt or net) else 1e-10, what=f"{name} G={G}")
+    eng.close()
+
+
 @pytest.mark.parametrize("name", round_golden_names())
 def test_replay_fp32_within_tolerance(name):
     gu = _gpu()
