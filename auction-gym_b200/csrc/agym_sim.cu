@@ -229,9 +229,9 @@ static int launch_d(agym_handle* h, const SimParams& p, const agym_replay_inputs
   // Lane-group width.  Everything outside the item loop (context, participants, resolution, click, accumulators: more than
   // half of the instructions at 64 items) is issued once per warp instruction whatever G is, so narrow groups -- more
   // opportunities per warp, more items per lane -- amortise it: B200, bench shape, G = 32 / 16 / 8 -> 10.6 / 7.7 / 7.2 ms
-  // (Oracle allocators 6.1 / 4.7 / 3.6 ms).  Small launches keep wide groups: they need the parallelism more.
-  int G = h->max_items > 16 ? 32 : (h->max_items > 8 ? 16 : 8);
-  if ((long long)p.n_runs * p.T >= 65536) G = 8;
+  // (Oracle allocators 6.1 / 4.7 / 3.6 ms).  The width is the same for every launch size (the Thompson noise of an item
+  // is addressed through its lane's position, so a launch-size-dependent width would break "chunked calls == one call").
+  int G = 8;
   if (const char* env = getenv("AGYM_SIM_G")) { const int v = atoi(env); if (v == 8 || v == 16 || v == 32) G = v; }  // experiment knob
   while (G < p.P) G *= 2;
   if (DMAX / 4 > G) G = 32;

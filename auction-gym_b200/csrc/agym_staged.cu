@@ -7,6 +7,8 @@
 //   K4 resolution + click        reads 13P, writes 10      = 36 B at P = 2
 // All four draw from the same Philox counters as the fused kernel, so K1->K2->K3->K4 reproduces the
 // fused FP32 results exactly.
+#include <cstdlib>
+
 #include "agym_round.cuh"
 
 namespace agym {
@@ -86,7 +88,9 @@ template <int DMAX>
 static int launch_k2_d(agym_handle* h, const SimParams& p, const float* ctx, const uint8_t* parts, uint8_t* item, float* est,
                        float* true_ctr, float* best_ev, float* value, cudaStream_t s) {
   const long long N = (long long)p.R * p.T;
-  int G = h->max_items > 16 ? 32 : (h->max_items > 8 ? 16 : 8);
+  int G = 8;  // the fused kernel's lane-group width (agym_sim.cu launch_d): same Thompson noise addressing
+  if (const char* env = getenv("AGYM_SIM_G")) { const int v = atoi(env); if (v == 8 || v == 16 || v == 32) G = v; }
+  while (G < p.P) G *= 2;
   if (DMAX / 4 > G) G = 32;
   const long long threads = N * G;
   const unsigned grid = unsigned((threads + 255) / 256);
