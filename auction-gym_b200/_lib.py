@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libagym.so")
+LIB_PATH = os.environ.get("AGYM_LIB_PATH") or os.path.join(_HERE, "libagym.so")  # the override is for A/B builds of the library
 
 NUM_METRICS = 12
 BIDDER_D = 4
