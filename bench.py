@@ -328,9 +328,9 @@ def main():
                 "note": f"{R * T} opportunities, {by / 1e6:.0f} MB algorithmic; L2 flushed (512 MB fill) before every timed launch; outside the timed step"}
         del b, flush
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures of exactly this
-    # shape (profiles/r1_fit_warp_ncu_full.txt, profiles/r1_sim_kernel_logit_ts_ncu_full.txt, profiles/r1_sim_kernel_k4_ncu_full.txt); null for any other shape
+    # shape (profiles/r1_fit_warp_ncu_full.txt, profiles/r1_sim_kernel_g8_ncu_full.txt, profiles/r1_sim_kernel_k4_ncu_full.txt); null for any other shape
     std_shape = R == WORKLOAD["runs_per_gpu"] and T == WORKLOAD["T"] and learnt
-    ncu_traffic = {"sim_kernel (fused K1-K5)": 88196352 + 64818688, "bucket_kernel + fit_kernel (K6)": 250489600 + 71059200,
+    ncu_traffic = {"sim_kernel (fused K1-K5)": 87358464 + 63195904, "bucket_kernel + fit_kernel (K6)": 250489600 + 71059200,
                    "k4_resolve+accumulate": 141547520 + 49876736} if std_shape else {}
     for k, v in {**kernels, **aux}.items():
         v["traffic"] = ncu_traffic.get(k)
