@@ -19,6 +19,8 @@
 // (seed, run, iteration, epoch, row), so a fit is reproducible and independent of the launch geometry.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "agym_common.cuh"
 
 namespace agym {
@@ -197,8 +199,8 @@ struct Trainer {
 // ------------------------------------------------------------------------------------------------
 // win-rate model (Models.py:51-62)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) winrate_fit_kernel(const BidFitParams p) {
-  constexpr int NT = 256;
+template <int NT>
+__global__ void __launch_bounds__(NT) winrate_fit_kernel(const BidFitParams p) {
   extern __shared__ __align__(16) float4 srow[];  // [ncap] {est, value, gamma, won}
   __shared__ float red[2 * (NT / 32) * 5];
   const int run = blockIdx.x / p.A, a = blockIdx.x % p.A;
@@ -314,8 +316,8 @@ __device__ __forceinline__ void policy_backward(const float (&th)[12], const Pol
 
 enum { kStageImitate = 0, kStageMain = 1 };
 
-__global__ void __launch_bounds__(256) policy_fit_kernel(const BidFitParams p) {
-  constexpr int NT = 256;
+template <int NT>
+__global__ void __launch_bounds__(NT) policy_fit_kernel(const BidFitParams p) {
   __shared__ float red[2 * (NT / 32) * 13];
   const int run = blockIdx.x / p.A, a = blockIdx.x % p.A;
   const int kind = p.fit_kind[a];
@@ -553,6 +555,10 @@ int launch_update_bidders(agym_handle* h, uint64_t seed, int iter, int max_epoch
   gather_rows_kernel<<<grid, 256, 0, s>>>(bp);
   int rc = check_cuda(h, cudaGetLastError(), "bidder fit prologue");
   if (rc) return rc;
+  // few fits (the shipped configs have 6 - 18): every CTA has an SM to itself and an epoch is a latency chain over the
+  // fit's rows, so wider CTAs shorten it; with many fits 256 threads keep more of them resident
+  bool wide = grid <= unsigned(h->num_sms);
+  if (const char* env = getenv("AGYM_BIDFIT_WIDE")) wide = atoi(env) != 0;  // experiment knob
   if (h->any_winrate_fit) {
     long long ncap = 2 * (Tn * sh.P / sh.A) + 64;  // expected rows per agent x 2
     if (ncap > Tn * sh.P) ncap = Tn * sh.P;
@@ -561,17 +567,24 @@ int launch_update_bidders(agym_handle* h, uint64_t seed, int iter, int max_epoch
     wp.ncap = int(ncap);
     wp.max_epochs = max_epochs > 0 && max_epochs < kAdamTable2 ? max_epochs : kAdamTable2;  // Bidder.py:240  epochs = 8192 * 4
     const size_t smem = (size_t)wp.ncap * sizeof(float4);
-    cudaError_t e = cudaFuncSetAttribute(winrate_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaError_t e;
+    if (wide) {
+      e = cudaFuncSetAttribute(winrate_fit_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e == cudaSuccess) winrate_fit_kernel<512><<<grid, 512, smem, s>>>(wp);
+    } else {
+      e = cudaFuncSetAttribute(winrate_fit_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e == cudaSuccess) winrate_fit_kernel<256><<<grid, 256, smem, s>>>(wp);
+    }
     if (e != cudaSuccess) return check_cuda(h, e, "winrate_fit_kernel attribute");
-    winrate_fit_kernel<<<grid, 256, smem, s>>>(wp);
     if ((rc = check_cuda(h, cudaGetLastError(), "winrate_fit_kernel"))) return rc;
   }
   if (h->any_policy_fit) {
     BidFitParams pp = bp;
-    pp.stage = kStageImitate;
-    policy_fit_kernel<<<grid, 256, 0, s>>>(pp);
-    pp.stage = kStageMain;
-    policy_fit_kernel<<<grid, 256, 0, s>>>(pp);
+    for (int stage = kStageImitate; stage <= kStageMain; ++stage) {
+      pp.stage = stage;
+      if (wide) policy_fit_kernel<512><<<grid, 512, 0, s>>>(pp);
+      else policy_fit_kernel<256><<<grid, 256, 0, s>>>(pp);
+    }
     if ((rc = check_cuda(h, cudaGetLastError(), "policy_fit_kernel"))) return rc;
   }
   if (h->any_empirical_fit) {
