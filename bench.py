@@ -383,7 +383,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                         "note": "same iterations of the same trajectory as `value` (restart from the initial host state, same warm-up); every step "
                                 "uploads the learnt state from pinned host memory and reads state + metrics back"},
-                "gpu_launches": args.steps * (3 if learnt else 1),
+                "gpu_launches": args.steps * (4 if learnt else 1),  # sim_kernel + bucket_kernel + fit_order_kernel + fit_warp_kernel per step
                 "round_loop": {"value": R * T * world / k_ms["rounds"] * 1e3 if k_ms["rounds"] else None, "unit": UNIT, "ms": k_ms["rounds"]},
                 "roofline": roofline, "roofline_kernels": {**kernels, **aux}, "cpu_baseline": cpu, "shipped_config": shipped, "clocks": clk}
         print(json.dumps(line), flush=True)
