@@ -1,0 +1,39 @@
+"""GPU: bench.py's own arm prints ONE JSON line with every key of the measurement contract (small shape, no CPU baseline)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bench_line_carries_the_contract_keys():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3", "--runs-per-gpu", "16", "--rounds", "2000",
+                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert d["metric"] == "auction opportunities/sec" and d["unit"] == "opportunities/s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3
+    assert d["scaling"] == "weak" and d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    opp = 16 * 2000
+    assert abs(d["value"] - opp / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and 0 < e["value"] <= d["value"] * 1.05 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert d["gpu_launches"] == 2 * 4
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    k4 = d["roofline_kernels"]["k4_resolve"]
+    assert k4["bound"] == "hbm" and 0 < k4["frac"] <= 1.2
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
