@@ -8,7 +8,7 @@
  *   *.allocate / estimate_CTR / Bidder.bid     reference src/AuctionAllocation.py:18-35,
  *                                              src/BidderAllocation.py:29-82, src/Bidder.py:28-208
  * The entry points below are what those Python classes bind (through ctypes, see
- * auction-gym_b200/_lib.py and INTEGRATION.md).  Conventions:
+ * auction_gym_b200/_lib.py and INTEGRATION.md).  Conventions:
  *   - plain C types only; no torch / C++ types cross the boundary;
  *   - every function returns 0 on success and a negative agym_status otherwise; the message is
  *     available from agym_last_error(); nothing throws across the ABI;

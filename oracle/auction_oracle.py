@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement (numpy) of AuctionGym's round loop in replay mode.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
-reference`` legs may import this module; the product path (``auction-gym_b200/``) never does.
+reference`` legs may import this module; the product path (``auction_gym_b200/``) never does.
 
 Parity pin: the reference ships no tests or golden vectors, so this
 restatement is pinned against OUTPUTS OF THE UNMODIFIED REFERENCE run in the build container

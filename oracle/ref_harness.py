@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- harness that drives the UNMODIFIED reference in replay mode.
 
 This file is part of ``oracle/`` (the checker).  Nothing in the product path
-(``auction-gym_b200/``) may import it.  It is only usable in the build container,
+(``auction_gym_b200/``) may import it.  It is only usable in the build container,
 where the reference tree is mounted read-only at ``/root/reference``; the GPU box
 has no such tree, so everything that runs there uses the committed fixtures in
 ``tests/golden/`` that ``oracle/make_golden.py`` produced with this harness.

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement of log retention across iterations (``Agent(memory=...)``).
 
 Part of ``oracle/`` (the checker): only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may import
-it; the product path (``auction-gym_b200/``) never does.
+it; the product path (``auction_gym_b200/``) never does.
 
 What the reference does (cited lines are of the unmodified reference):
   * ``Agent.clear_logs`` (src/Agent.py:124-129): ``self.logs = self.logs[-self.memory:]`` when ``memory`` is set, else

@@ -71,7 +71,7 @@ def test_no_cpu_fallback():
 
 def test_product_path_does_not_touch_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py may import oracle/."""
-    pkg = os.path.join(ROOT, "auction-gym_b200")
+    pkg = os.path.join(ROOT, "auction_gym_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
@@ -98,7 +98,7 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
         "  printf(\"%d %d %d %s\\n\", agym_abi_version(), bad, bad2, agym_last_error(0));\n"
         "  return (agym_abi_version() == AGYM_ABI_VERSION && bad == AGYM_ERR_INVALID && bad2 == AGYM_ERR_INVALID) ? 0 : 1;\n}\n")
     exe = tmp_path / "abi"
-    libdir = os.path.join(ROOT, "auction-gym_b200")
+    libdir = os.path.join(ROOT, "auction_gym_b200")
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                     "-L", libdir, "-lagym", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout

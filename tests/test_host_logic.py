@@ -110,7 +110,7 @@ def test_csv_schema(tmp_path):
 
 
 def test_bare_name_modules_like_the_reference():
-    sys.path.insert(0, os.path.join(ROOT, "auction-gym_b200", "src"))
+    sys.path.insert(0, os.path.join(ROOT, "auction_gym_b200", "src"))
     try:
         import importlib
 

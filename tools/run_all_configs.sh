@@ -3,7 +3,7 @@
 mkdir -p gpurun_out/configs
 for c in SP_Oracle SP_Truthful_TS FP_DM_Oracle FP_DM_TS FP_DR_TS FP_IPS_TS; do
   s=$(date +%s%N)
-  python auction-gym_b200/src/main.py config/$c.json --output-dir gpurun_out/configs/$c > gpurun_out/configs/$c.log 2>&1
+  python auction_gym_b200/src/main.py config/$c.json --output-dir gpurun_out/configs/$c > gpurun_out/configs/$c.log 2>&1
   rc=$?
   e=$(date +%s%N)
   echo "$c rc=$rc wall=$(( (e - s) / 1000000 )) ms"
