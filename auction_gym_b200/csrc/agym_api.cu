@@ -90,6 +90,7 @@ int agym_create(const agym_shape* shape, int device, agym_handle** out) {
             cudaMalloc(&h->d_V32, nV * sizeof(float)) == cudaSuccess &&
             cudaMalloc(&h->d_adam_sz0, kAdamTable * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->d_adam_bc2s, kAdamTable * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&h->d_adam_ep, kAdamTable * sizeof(float2)) == cudaSuccess &&
             cudaMalloc(&h->d_adam_bc1, kAdamTable2 * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->d_adam_bc2s2, kAdamTable2 * sizeof(float)) == cudaSuccess;
   if (ok) {
@@ -101,6 +102,8 @@ int agym_create(const agym_shape* shape, int device, agym_handle** out) {
       sz0[e] = 2e-3 / (1.0 - std::pow(0.9, t));
       bc2s[e] = float(std::sqrt(1.0 - std::pow(0.999, t)));
     }
+    std::vector<float2> ep(kAdamTable);
+    for (int e = 0; e < kAdamTable; ++e) ep[e] = make_float2(float(sz0[e]), bc2s[e]);
     std::vector<double> bc1(kAdamTable2);
     std::vector<float> bc2s2(kAdamTable2);
     for (int e = 0; e < kAdamTable2; ++e) {
@@ -111,7 +114,8 @@ int agym_create(const agym_shape* shape, int device, agym_handle** out) {
     ok = cudaMemcpy(h->d_adam_bc1, bc1.data(), kAdamTable2 * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(h->d_adam_bc2s2, bc2s2.data(), kAdamTable2 * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(h->d_adam_sz0, sz0.data(), kAdamTable * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
-         cudaMemcpy(h->d_adam_bc2s, bc2s.data(), kAdamTable * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+         cudaMemcpy(h->d_adam_bc2s, bc2s.data(), kAdamTable * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(h->d_adam_ep, ep.data(), kAdamTable * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
   }
   if (!ok) {
     set_error(nullptr, AGYM_ERR_CUDA, std::string("agym_create: cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -128,7 +132,10 @@ int agym_destroy(agym_handle* h) {
   cudaFree(h->d_n_items); cudaFree(h->d_alloc_kind); cudaFree(h->d_bidder_kind); cudaFree(h->d_bidder_fit);
   cudaFree(h->d_E64); cudaFree(h->d_V64); cudaFree(h->d_E32); cudaFree(h->d_V32);
   cudaFree(h->d_memory); cudaFree(h->d_mem_off);
-  cudaFree(h->d_adam_sz0); cudaFree(h->d_adam_bc2s); cudaFree(h->k4_scratch); cudaFree(h->d_adam_bc1); cudaFree(h->d_adam_bc2s2);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  cudaFree(h->d_adam_sz0); cudaFree(h->d_adam_bc2s); cudaFree(h->d_adam_ep); cudaFree(h->k4_scratch); cudaFree(h->d_adam_bc1); cudaFree(h->d_adam_bc2s2);
   delete h;
   return AGYM_OK;
 }
@@ -376,6 +383,14 @@ int agym_retain_logs(agym_handle* h, void* stream) {
   const int rc = launch_retain_logs(h, (cudaStream_t)stream);
   if (rc == AGYM_OK) h->rounds_in_iter = 0;
   return rc;
+}
+
+int agym_set_option(agym_handle* h, const char* name, double value) {
+  if (!h || !name) return AGYM_ERR_INVALID;
+  static const char* const known[] = {"fit_dense", "fit_nt", "fit_ncap", "fit_warp", "fit_heavy", "sim_g", "bidfit_wide"};
+  for (const char* k : known)
+    if (std::string(k) == name) { h->options[name] = value; return AGYM_OK; }
+  return set_error(h, AGYM_ERR_INVALID, std::string("agym_set_option: unknown option '") + name + "'");
 }
 
 int agym_update_allocators(agym_handle* h, int32_t fit_mode, int32_t max_epochs, float* fit_info, void* stream) {

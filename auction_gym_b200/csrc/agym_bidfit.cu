@@ -558,7 +558,7 @@ int launch_update_bidders(agym_handle* h, uint64_t seed, int iter, int max_epoch
   // few fits (the shipped configs have 6 - 18): every CTA has an SM to itself and an epoch is a latency chain over the
   // fit's rows, so wider CTAs shorten it; with many fits 256 threads keep more of them resident
   bool wide = grid <= unsigned(h->num_sms);
-  if (const char* env = getenv("AGYM_BIDFIT_WIDE")) wide = atoi(env) != 0;  // experiment knob
+  if (h->has_option("bidfit_wide")) wide = h->option("bidfit_wide", 0) != 0;
   if (h->any_winrate_fit) {
     long long ncap = 2 * (Tn * sh.P / sh.A) + 64;  // expected rows per agent x 2
     if (ncap > Tn * sh.P) ncap = Tn * sh.P;

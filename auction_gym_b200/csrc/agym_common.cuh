@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
 
 #include "agym.h"
@@ -197,7 +198,8 @@ struct agym_handle {
   double* d_adam_bc1 = nullptr;  // [kAdamTable2] 1 - 0.9^t
   float* d_adam_bc2s2 = nullptr; // [kAdamTable2] sqrt(1 - 0.999^t)
   double* d_adam_sz0 = nullptr;  // [kAdamTable] 2e-3 / (1 - 0.9^t), t = epoch + 1 (torch Adam step size at lr 2e-3)
-  float* d_adam_bc2s = nullptr;
+  float* d_adam_bc2s = nullptr;  // [kAdamTable] sqrt(1 - 0.999^t)
+  float2* d_adam_ep = nullptr;   // [kAdamTable] {float(d_adam_sz0), d_adam_bc2s}: one 64-bit load per epoch
   float* k4_scratch = nullptr;   // [R][A][8 buckets][8] float partial sums of the staged resolution kernel (lazy)  // [kAdamTable] sqrt(1 - 0.999^t)
   bool agents_set = false, catalog_set = false;
   bool any_learnt = false, any_shaded = false;
@@ -225,6 +227,13 @@ struct agym_handle {
   double* terms = nullptr;   // borrowed
   int64_t log_base = 0;      // sum(memory)
   int num_sms = 148;
+  // second stream for kernels that run beside each other inside one call (fork / join with events; created on first use)
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // kernel-selection / tuning overrides set through agym_set_option (tests and experiments; never the environment)
+  std::map<std::string, double> options;
+  bool has_option(const char* k) const { return options.count(k) != 0; }
+  double option(const char* k, double dflt) const { auto it = options.find(k); return it == options.end() ? dflt : it->second; }
   std::string err;
 };
 

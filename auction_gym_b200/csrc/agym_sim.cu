@@ -232,7 +232,7 @@ static int launch_d(agym_handle* h, const SimParams& p, const agym_replay_inputs
   // (Oracle allocators 6.1 / 4.7 / 3.6 ms).  The width is the same for every launch size (the Thompson noise of an item
   // is addressed through its lane's position, so a launch-size-dependent width would break "chunked calls == one call").
   int G = 8;
-  if (const char* env = getenv("AGYM_SIM_G")) { const int v = atoi(env); if (v == 8 || v == 16 || v == 32) G = v; }  // experiment knob
+  if (h->has_option("sim_g")) { const int v = int(h->option("sim_g", 8)); if (v == 8 || v == 16 || v == 32) G = v; }  // tests: every width
   while (G < p.P) G *= 2;
   if (DMAX / 4 > G) G = 32;
   switch (G) {

@@ -89,7 +89,7 @@ static int launch_k2_d(agym_handle* h, const SimParams& p, const float* ctx, con
                        float* true_ctr, float* best_ev, float* value, cudaStream_t s) {
   const long long N = (long long)p.R * p.T;
   int G = 8;  // the fused kernel's lane-group width (agym_sim.cu launch_d): same Thompson noise addressing
-  if (const char* env = getenv("AGYM_SIM_G")) { const int v = atoi(env); if (v == 8 || v == 16 || v == 32) G = v; }
+  if (h->has_option("sim_g")) { const int v = int(h->option("sim_g", 8)); if (v == 8 || v == 16 || v == 32) G = v; }
   while (G < p.P) G *= 2;
   if (DMAX / 4 > G) G = 32;
   const long long threads = N * G;

@@ -8,10 +8,13 @@ OUT="$HERE/../libagym.so"
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -cudart static -I$ROOT/include -I$HERE"
 mkdir -p "$HERE/obj"
 pids=()
-for f in agym_api agym_sim agym_staged agym_fit agym_bidfit agym_retain; do
+SRCS="agym_api agym_sim agym_staged agym_fit agym_fit_warp agym_bidfit agym_retain"
+OBJS=""
+for f in $SRCS; do
+  OBJS="$OBJS $HERE/obj/$f.o"
   $NVCC $FLAGS ${AGYM_PTXAS_V:+-Xptxas -v} -c "$HERE/$f.cu" -o "$HERE/obj/$f.o" &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -cudart static -gencode arch=compute_100a,code=sm_100a -o "$OUT" "$HERE"/obj/*.o
+$NVCC -shared -cudart static -gencode arch=compute_100a,code=sm_100a -o "$OUT" $OBJS
 echo "built $OUT"

@@ -191,6 +191,13 @@ int64_t agym_retained_capacity(const agym_handle* h);
  * Net / gross utility and revenue are NOT touched (Agent.clear_utility and Auction.clear_revenue are separate calls). */
 int agym_retain_logs(agym_handle* h, void* stream);
 
+/* Kernel-selection overrides for tests and experiments (the library never reads the environment): "fit_warp" 0 = CTA
+ * fit kernels only, "fit_dense" 0/1, "fit_nt" threads per CTA, "fit_ncap" rows staged per fit as a multiple of the mean,
+ * "fit_heavy" whole-warp threshold of the CTA kernel, "sim_g" lane-group width of the round loop (8, 16, 32),
+ * "bidfit_wide" 0/1.  They choose between implementations of the same function (the reference has one:
+ * BidderAllocation.py:29-65, Auction.py:28-74, Bidder.py:210-615); unknown names are AGYM_ERR_INVALID. */
+int agym_set_option(agym_handle* h, const char* name, double value);
+
 /* ---- per-iteration model updates ---- */
 enum agym_fit_mode {
   AGYM_FIT_ADAM_REF = 0,  /* IEEE divide / sqrt, accurate expf / logf: the operations torch's CPU kernels perform */

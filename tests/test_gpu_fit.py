@@ -174,27 +174,25 @@ def test_rounds_then_fit_end_to_end():
     eng.close()
 
 
-KERNEL_VARIANTS = {
-    "warp": {},                                                   # fit_warp_kernel (the default for this shape)
-    "warp_heavy4": {"AGYM_FIT_HEAVY": "4"},                       # ... with most items on the whole-warp path
-    "warp_overflow": {"AGYM_FIT_NCAP": "0.5"},                    # ... with half of the rows in the global overflow arrays
-    "cta64": {"AGYM_FIT_WARP": "0"},                              # fit_rows_kernel<5, ., 128>
-    "cta64_heavy4": {"AGYM_FIT_WARP": "0", "AGYM_FIT_HEAVY": "4"},
-    "cta_big": {"AGYM_FIT_WARP": "0", "AGYM_FIT_NT": "256"},      # fit_rows_kernel<5, false, 1024>: chunked segment sums
-    "dense": {"AGYM_FIT_WARP": "0", "AGYM_FIT_DENSE": "1"},       # fit_items_kernel: a warp per item
+KERNEL_VARIANTS = {  # Engine.set_option overrides (include/agym.h: agym_set_option)
+    "warp": {},                                      # fit_warp_kernel (the default for this shape)
+    "warp_overflow": {"fit_ncap": 0.5},              # ... with half of the rows left in the global workspace
+    "warp_tiny_smem": {"fit_ncap": 0.1},             # ... with one staged iteration only
+    "cta64": {"fit_warp": 0},                        # fit_rows_kernel<5, ., 128>
+    "cta64_heavy4": {"fit_warp": 0, "fit_heavy": 4},
+    "cta_big": {"fit_warp": 0, "fit_nt": 256},       # fit_rows_kernel<5, false, 1024>: chunked segment sums
+    "dense": {"fit_warp": 0, "fit_dense": 1},        # fit_items_kernel: a warp per item
 }
 
 
 @pytest.mark.parametrize("variant", list(KERNEL_VARIANTS))
 @pytest.mark.parametrize("name", ["fit_ref_shape", "fit_64x64"])
-def test_every_fit_kernel_matches_the_oracle_on_a_fixed_budget(name, variant, monkeypatch):
+def test_every_fit_kernel_matches_the_oracle_on_a_fixed_budget(name, variant):
     """All K6 kernels implement the same state machine: with a fixed epoch budget (no chaotic stop) each of them must land
     on the fit oracle's parameters, whichever one the launcher's shape heuristic would have picked."""
     import torch
 
     gu = _gpu()
-    for k, v in KERNEL_VARIANTS[variant].items():
-        monkeypatch.setenv(k, v)
     z = np.load(f"{GOLDEN_DIR}/{name}.npz")
     agents = [int(a) for a in z["fit_agents"]]
     pre = [f"it1_a{a}_" for a in agents]
@@ -207,6 +205,8 @@ def test_every_fit_kernel_matches_the_oracle_on_a_fixed_budget(name, variant, mo
     rows.sort(key=lambda t: (t[0], t[1]))
     T = len(rows)
     eng = _engine_for_fits(gu, len(agents), I, Do, T)
+    for k, v in KERNEL_VARIANTS[variant].items():
+        eng.set_option(k, v)
     eng.fit_ctx[0, :T].copy_(torch.from_numpy(np.stack([r[2] for r in rows]).astype(np.float32)))
     meta = _pack_meta(np.array([r[1] for r in rows]), np.array([r[3] for r in rows]), np.array([r[4] for r in rows]) > 0)
     eng.fit_meta[0, :T].copy_(torch.from_numpy(meta.view(np.int32)))

@@ -64,7 +64,7 @@ def test_bench_shape_invariants():
     eng.close()
 
 
-def test_two_independent_fit_kernels_agree_at_the_bench_shape(monkeypatch):
+def test_two_independent_fit_kernels_agree_at_the_bench_shape():
     """The warp-per-fit kernel (default) and the CTA kernel are separate implementations of the same optimiser.  On the
     bench shape with the reference's full epoch budget they must reach the same optimum: final losses within 5e-4 rel
     (items whose rows are all non-clicks have no finite optimum -- their intercept drifts until the stop rule fires),
@@ -82,13 +82,11 @@ def test_two_independent_fit_kernels_agree_at_the_bench_shape(monkeypatch):
     E, V = ao.make_catalog(np.random.default_rng(0), A, I, D)
     m0 = torch.randn(R, A, I, Do + 1, generator=torch.Generator().manual_seed(5))
     out = {}
-    for name, env in (("warp", None), ("warp_again", None), ("cta", "0")):
-        if env is None:
-            monkeypatch.delenv("AGYM_FIT_WARP", raising=False)
-        else:
-            monkeypatch.setenv("AGYM_FIT_WARP", env)
+    for name, warp in (("warp", None), ("warp_again", None), ("cta", 0)):
         eng = ag.Engine(R=R, A=A, I=I, D=D, Do=Do, P=P, mechanism=_lib.SECOND_PRICE, E=E, V=V, n_items=[I] * A,
                         alloc_kind=[_lib.ALLOC_TS] * A, bidder_kind=[_lib.BID_TRUTHFUL] * A, rounds_capacity=T)
+        if warp is not None:
+            eng.set_option("fit_warp", warp)
         eng.set_allocator_state(m0)
         for it in range(2):  # second iteration: rows concentrated on few items per agent
             eng.clear_iteration()

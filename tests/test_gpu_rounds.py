@@ -56,15 +56,15 @@ def test_replay_fp64_matches_oracle_and_reference(name):
 
 @pytest.mark.parametrize("G", ["8", "16", "32"])
 @pytest.mark.parametrize("name", ["rounds_sp_ts_64x64", "rounds_sp_oracle_64x64", "rounds_fp_pA", "rounds_sp_ragged", "rounds_fp_search", "rounds_fp_bandit"])
-def test_replay_is_exact_for_every_lane_group_width(name, G, monkeypatch):
+def test_replay_is_exact_for_every_lane_group_width(name, G):
     """The launcher picks the lane-group width from the catalog width and the launch size (8 lanes for large launches);
-    every width must reproduce the reference's discrete decisions -- forced here through the AGYM_SIM_G experiment knob."""
+    every width must reproduce the reference's discrete decisions -- forced here through the "sim_g" option (agym_set_option)."""
     gu = _gpu()
     from auction_gym_b200 import _lib
 
-    monkeypatch.setenv("AGYM_SIM_G", G)
     case, inp, ref, met = load_golden(name)
     eng = gu.engine_from_case(case, R=1, precision=_lib.FP64)
+    eng.set_option("sim_g", int(G))
     got = gu.log_to_numpy(gu.replay_case(eng, inp))
     rec, m = ao.simulate_rounds(case, inp["ctx"], inp["parts"], inp["u"], inp.get("ts_eps"), inp.get("gamma_z"), inp.get("grid_u"))
     learnt = bool((case["alloc_kind"] != ao.ALLOC_ORACLE).any())

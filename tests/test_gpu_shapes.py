@@ -91,16 +91,16 @@ def test_odd_shapes_replay_and_fit(name):
 
 @pytest.mark.parametrize("ncap", ["0.3", "1.5"])
 @pytest.mark.parametrize("shape", [(64, 64, 6000), (6, 12, 3000)])  # sparse-kernel regime, dense-kernel regime
-def test_fit_overflow_rows_and_both_kernels(shape, ncap, monkeypatch):
-    """AGYM_FIT_NCAP shrinks the rows staged in shared memory so most rows take the global overflow path."""
+def test_fit_overflow_rows_and_both_kernels(shape, ncap):
+    """The "fit_ncap" option shrinks the rows staged in shared memory so most rows take the global overflow path."""
     gu = _gpu()
     from auction_gym_b200 import _lib
 
     A, I, T = shape
-    monkeypatch.setenv("AGYM_FIT_NCAP", ncap)
     case, rng = _case(7, A=A, n_items=I, D=5, Do=4, P=2, mech=ao.MECH_SECOND, alloc=[1] * A, bid=[0] * A)
     nz = ao.draw_replay_inputs(rng, T, A, 2, 5, I, 4, 0.8, want_eps=True)
     eng = gu.engine_from_case(case, R=2, precision=_lib.FP64)
+    eng.set_option("fit_ncap", float(ncap))
     eng.replay(np.stack([nz["ctx"]] * 2), np.stack([nz["parts"]] * 2), np.stack([nz["u"]] * 2), ts_eps=np.stack([nz["ts_eps"]] * 2))
     info = eng.update_allocators(max_epochs=120).cpu().numpy()
     rec, _ = ao.simulate_rounds(case, nz["ctx"], nz["parts"], nz["u"], nz["ts_eps"])
