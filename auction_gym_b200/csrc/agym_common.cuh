@@ -228,6 +228,8 @@ struct agym_handle {
   int64_t log_base = 0;      // sum(memory)
   int num_sms = 148;
   // second stream for kernels that run beside each other inside one call (fork / join with events; created on first use)
+  int* d_fit_epochs = nullptr;   // [R*A] epochs of each allocator fit in the previous update (launch-order hint, owned)
+  size_t fit_epochs_len = 0;
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // kernel-selection / tuning overrides set through agym_set_option (tests and experiments; never the environment)

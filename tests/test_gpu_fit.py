@@ -1,11 +1,16 @@
 """GPU parity of the per-iteration allocator fit (K6) through the C ABI.
 
-Tolerances (evidence in BASELINE.md): the reference's Adam + plateau scheduler +
-early-stop trajectory is chaotic at the 1e-3 level (permuting its own training rows moves m by 8.8e-4),
-so fitted parameters are compared at |dm| <= 1e-2 abs, q <= 2e-3 rel and the stop epoch at +-2 % (+-25).
-q is the Laplace precision evaluated at the fitted m (q += sum P(1-P) x^2, Models.py:43-45), so it inherits m's spread:
-an independent float32 restatement of the reference lands within 6e-4..9.5e-4 of torch, and a different
-summation order on the device (stop epoch 1227 vs 1237) has been seen at 1.15e-3.
+Tolerances (evidence in BASELINE.md): the reference's Adam + plateau scheduler + early-stop
+trajectory is chaotic at the 1e-3 level -- permuting its own training rows moves m by 8.8e-4 and the stop epoch by 5-11,
+and an independent float32 restatement lands within +-18 epochs of torch.  The bars, with what the device measured
+against the reference-run goldens (tools/fit_parity_report.py, profiles/r2_fit_parity_report.txt):
+  * fitted m: |dm| <= 1e-2 abs                       (measured max 7.0e-3; the fit oracle itself: 9.7e-3)
+  * stop epoch: +-1 % with a floor of +-20 epochs    (measured max 18 of 1086 and 41 of 4280)
+  * q: <= 1.5e-3 rel.  q is the Laplace precision evaluated at the fitted m (q += sum P(1-P) x^2, Models.py:43-45), so it
+    inherits m's spread: 13 of 14 cases are within 9.1e-4 (the fit oracle itself: 9.5e-4); the one at 1.15e-3 is a fit
+    that stops 11 epochs early (1226 vs 1237), the shift the reference shows when its own rows are permuted
+  * downstream MAP CTR on a fixed context batch: <= 3e-2 rel.  d(ctr)/ctr ~ |x|_1 |dm| with |x|_1 ~ 3, so this is the m
+    bar restated (measured max 2.1e-2 where |dm| = 7.0e-3; the fit oracle against the reference: 2.9e-2)
 """
 import numpy as np
 import pytest
@@ -16,7 +21,7 @@ from tests.conftest import GOLDEN_DIR, load_golden
 
 pytestmark = pytest.mark.gpu
 
-M_ATOL, Q_RTOL = 1e-2, 2e-3
+M_ATOL, Q_RTOL, CTR_RTOL = 1e-2, 1.5e-3, 3e-2
 
 
 def _gpu():
@@ -46,7 +51,7 @@ def _engine_for_fits(gu, n_agents, I, Do, T, R=1):
 def _stop_close(got, want):
     # permuting the reference's own rows moves its stop epoch by 5-11, an independent float32
     # restatement lands within +-18; a different reduction tree on the device is the same kind of perturbation
-    return abs(got - want) <= max(25, 0.02 * want)
+    return abs(got - want) <= max(20, 0.01 * want)
 
 
 @pytest.mark.parametrize("name", ["fit_ref_shape", "fit_64x64"])
@@ -100,7 +105,7 @@ def test_fit_matches_reference_and_oracle(name, it, fit_mode):
         est_c = 1 / (1 + np.exp(-(xs @ m1[j].T)))
         est_r = 1 / (1 + np.exp(-(xs @ z[p + "m1"].T)))
         used = np.unique(z[p + "items"])
-        np.testing.assert_allclose(est_c[:, used], est_r[:, used], rtol=2e-2, atol=1e-4, err_msg=what)
+        np.testing.assert_allclose(est_c[:, used], est_r[:, used], rtol=CTR_RTOL, atol=1e-4, err_msg=what)
         # items without rows keep m and q bit-for-bit (Adam sees a zero gradient)
         unused = np.setdiff1d(np.arange(I), used)
         assert np.array_equal(m1[j][unused], z[p + "m0"][unused]) and np.array_equal(q1[j][unused], z[p + "q0"][unused])

@@ -17,6 +17,7 @@ for kv in filter(None, os.environ.get("FIT_OPTS", "").split(",")):
 eng.set_allocator_state(torch.randn(R, A, I, Do + 1, generator=torch.Generator().manual_seed(0)))
 mode = int(os.environ.get("FIT_MODE", "0"))
 tot = 0.0
+prev_ep = None
 for it in range(N):
     eng.clear_iteration()
     eng.simulate(1, it, T)
@@ -29,7 +30,11 @@ for it in range(N):
     torch.cuda.synchronize(); dt = time.time() - t0
     tot += dt
     n = info[..., 3]
+    ep = info[..., 1].flatten().double()
+    corr = float(torch.corrcoef(torch.stack([ep, prev_ep]))[0, 1]) if prev_ep is not None else float("nan")
+    prev_ep = ep
     print(f"it {it:3d}  {dt * 1e3:7.1f} ms  epochs mean {info[..., 1].mean().item():7.0f} max {info[..., 1].max().item():6.0f}  "
           f"rows mean {n.mean().item():5.0f} p99 {n.flatten().kthvalue(int(0.99 * n.numel())).values.item():4.0f} max {n.max().item():4.0f}  "
-          f"active items mean {n_active.mean().item():5.1f} max {n_active.max().item():3.0f}", flush=True)
+          f"active items mean {n_active.mean().item():5.1f} max {n_active.max().item():3.0f} >12 {(n_active > 12).float().mean().item():.3f} "
+          f">19 {(n_active > 19).float().mean().item():.3f}  epoch corr with previous {corr:.2f}", flush=True)
 print(f"total {tot * 1e3:.0f} ms over {N} iterations; checksum {eng.m.double().sum().item():.4f}")
