@@ -21,7 +21,7 @@ class Auction:
 
     def __init__(self, rng, allocation, agents, agent2items, agents2item_values, max_slots, embedding_size, embedding_var,
                  obs_embedding_size, num_participants_per_round, *, num_runs=1, run_offset=0, device=0, precision=None,
-                 seed=None, init_seed=None, rounds_capacity=0):
+                 seed=None, init_seed=None, rounds_capacity=0, per_run_init=None):
         if max_slots != 1:
             raise NotImplementedError("multi-slot auctions are not supported (src/main.py:36-37 says the same of the reference)")
         self.rng = rng
@@ -42,6 +42,10 @@ class Auction:
             seed = int(rng.integers(0, 2**62)) if hasattr(rng, "integers") and hasattr(rng, "bit_generator") else 0
         self.seed = int(seed)
         self.init_seed = self.seed if init_seed is None else int(init_seed)
+        # Initial model state.  per_run_init = True (the batched driver, any shard): every draw is seeded by the GLOBAL run
+        # index, so run r starts from the same state whichever rank owns it.  False (the reference's own calling pattern, one
+        # run driven from Python): the allocator's constructor draw, from the rng the caller passed, as Models.py:21-24 does.
+        self.per_run_init = bool(self.num_runs > 1 or self.run_offset) if per_run_init is None else bool(per_run_init)
         self.iteration = 0
         self.engine = None
         self._rounds_capacity = int(rounds_capacity)
@@ -79,7 +83,7 @@ class Auction:
             q = np.ones_like(m)
             for r in range(self.num_runs):
                 # one independent initialisation per run (the reference re-instantiates its agents per run, main.py:188)
-                rr = np.random.default_rng([self.init_seed, self.run_offset + r, 0x6d30]) if self.num_runs > 1 or self.run_offset else None
+                rr = np.random.default_rng([self.init_seed, self.run_offset + r, 0x6d30]) if self.per_run_init else None
                 for a, ag in enumerate(self.agents):
                     if isinstance(ag.allocator, OracleAllocator):
                         continue
@@ -92,9 +96,12 @@ class Auction:
             sg = np.array([ag.bidder._gamma_params()[1] for ag in self.agents])
             # PyTorchWinRateEstimator = Linear(3, 1): torch's default init is U(-1/sqrt(3), 1/sqrt(3)) for weight and bias
             # (Models.py:55-58); one independent draw per (run, agent), from the seed instead of torch's global generator
-            wr = np.random.default_rng([self.init_seed, self.run_offset, 0x7772]).uniform(-1, 1, (self.num_runs, A, 4)) / np.sqrt(3.0)
+            # (keyed by the global run index: a shard starts its runs from the same weights as a single-device job)
+            wr = np.stack([np.random.default_rng([self.init_seed, self.run_offset + r, 0x7772]).uniform(-1, 1, (A, 4))
+                           for r in range(self.num_runs)]) / np.sqrt(3.0)
             # policy nets (Models.py:71-77,97-101): Linear layers with fan-in 2 -> U(-1/sqrt(2), 1/sqrt(2))
-            pw = np.random.default_rng([self.init_seed, self.run_offset, 0x706f]).uniform(-1, 1, (self.num_runs, A, 12)) / np.sqrt(2.0)
+            pw = np.stack([np.random.default_rng([self.init_seed, self.run_offset + r, 0x706f]).uniform(-1, 1, (A, 12))
+                           for r in range(self.num_runs)]) / np.sqrt(2.0)
             eng.set_bidder_state(pg[None, :], sg[None, :], winrate_w=wr, policy_w=pw)
         self.engine = eng
         self.D_ctx = [D if isinstance(ag.allocator, OracleAllocator) else Do for ag in self.agents]  # Auction.py:46-49

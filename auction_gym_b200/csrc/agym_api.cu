@@ -386,6 +386,8 @@ int agym_retain_logs(agym_handle* h, void* stream) {
   return rc;
 }
 
+uint64_t agym_launch_count(const agym_handle* h) { return h ? h->launches : 0; }
+
 int agym_set_option(agym_handle* h, const char* name, double value) {
   if (!h || !name) return AGYM_ERR_INVALID;
   static const char* const known[] = {"fit_dense", "fit_nt", "fit_ncap", "fit_warp", "fit_heavy", "sim_g", "bidfit_wide"};

@@ -553,6 +553,7 @@ int launch_update_bidders(agym_handle* h, uint64_t seed, int iter, int max_epoch
   const unsigned grid = unsigned(sh.R) * unsigned(sh.A);
   bidrows_bucket_kernel<<<sh.R, 256, (2 * sh.A + 1) * sizeof(int), s>>>(bp);
   gather_rows_kernel<<<grid, 256, 0, s>>>(bp);
+  h->launches += 2;
   int rc = check_cuda(h, cudaGetLastError(), "bidder fit prologue");
   if (rc) return rc;
   // few fits (the shipped configs have 6 - 18): every CTA has an SM to itself and an epoch is a latency chain over the
@@ -576,6 +577,7 @@ int launch_update_bidders(agym_handle* h, uint64_t seed, int iter, int max_epoch
       if (e == cudaSuccess) winrate_fit_kernel<256><<<grid, 256, smem, s>>>(wp);
     }
     if (e != cudaSuccess) return check_cuda(h, e, "winrate_fit_kernel attribute");
+    h->launches += 1;
     if ((rc = check_cuda(h, cudaGetLastError(), "winrate_fit_kernel"))) return rc;
   }
   if (h->any_policy_fit) {
@@ -585,10 +587,12 @@ int launch_update_bidders(agym_handle* h, uint64_t seed, int iter, int max_epoch
       if (wide) policy_fit_kernel<512><<<grid, 512, 0, s>>>(pp);
       else policy_fit_kernel<256><<<grid, 256, 0, s>>>(pp);
     }
+    h->launches += 2;
     if ((rc = check_cuda(h, cudaGetLastError(), "policy_fit_kernel"))) return rc;
   }
   if (h->any_empirical_fit) {
     empirical_update_kernel<<<grid, 256, 0, s>>>(bp);
+    h->launches += 1;
     if ((rc = check_cuda(h, cudaGetLastError(), "empirical_update_kernel"))) return rc;
   }
   return AGYM_OK;

@@ -227,6 +227,7 @@ struct agym_handle {
   double* terms = nullptr;   // borrowed
   int64_t log_base = 0;      // sum(memory)
   int num_sms = 148;
+  unsigned long long launches = 0;  // kernels of this library launched through this handle (agym_launch_count)
   // second stream for kernels that run beside each other inside one call (fork / join with events; created on first use)
   int* d_fit_epochs = nullptr;   // [R*A] epochs of each allocator fit in the previous update (launch-order hint, owned)
   size_t fit_epochs_len = 0;

@@ -128,6 +128,7 @@ int launch_retain_logs(agym_handle* h, cudaStream_t s) {
   rp.acc = h->acc;
   if (sh.R > 65535) return set_error(h, AGYM_ERR_UNSUPPORTED, "agym_retain_logs: more than 65535 resident runs");
   retain_kernel<<<dim3(unsigned(sh.A), unsigned(sh.R)), 32, 0, s>>>(rp);
+  h->launches += 1;
   return check_cuda(h, cudaGetLastError(), "retain_kernel");
 }
 

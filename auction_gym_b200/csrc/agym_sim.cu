@@ -193,6 +193,7 @@ int launch_refresh_sigma(agym_handle* h, cudaStream_t s) {
   if (!h->q || !h->sigma) return set_error(h, AGYM_ERR_STATE, "agym_refresh_sigma: allocator state not bound");
   const size_t n = (size_t)h->shape.R * h->shape.A * h->shape.I * h->K;
   refresh_sigma_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(h->q, h->sigma, n);
+  h->launches += 1;
   return check_cuda(h, cudaGetLastError(), "refresh_sigma");
 }
 
@@ -221,6 +222,7 @@ static int launch_g(agym_handle* h, const SimParams& p, const agym_replay_inputs
     if (std_shape) sim_kernel<Real, G, DMAX, false, (DMAX == 8 ? 5 : 0), (DMAX == 8 ? 4 : 0)><<<unsigned(grid), threads, 0, s>>>(q, ri, lg);
     else sim_kernel<Real, G, DMAX, false, 0, 0><<<unsigned(grid), threads, 0, s>>>(q, ri, lg);
   }
+  h->launches += 1;
   return check_cuda(h, cudaGetLastError(), "sim_kernel launch");
 }
 

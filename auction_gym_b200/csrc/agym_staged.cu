@@ -39,6 +39,7 @@ int launch_k1(agym_handle* h, const SimParams& p, float* ctx, uint8_t* parts, cu
   if (p.P > kMaxP) return set_error(h, AGYM_ERR_UNSUPPORTED, "K1: P > 32");
   const long long N = (long long)p.R * p.T;
   k1_kernel<<<unsigned((N + 255) / 256), 256, 0, s>>>(p, ctx, parts, N);
+  h->launches += 1;
   return check_cuda(h, cudaGetLastError(), "k1_kernel");
 }
 
@@ -97,6 +98,7 @@ static int launch_k2_d(agym_handle* h, const SimParams& p, const float* ctx, con
   if (G == 8) k2_kernel<8, DMAX><<<grid, 256, 0, s>>>(p, ctx, parts, item, est, true_ctr, best_ev, value, N);
   else if (G == 16) k2_kernel<16, DMAX><<<grid, 256, 0, s>>>(p, ctx, parts, item, est, true_ctr, best_ev, value, N);
   else k2_kernel<32, DMAX><<<grid, 256, 0, s>>>(p, ctx, parts, item, est, true_ctr, best_ev, value, N);
+  h->launches += 1;
   return check_cuda(h, cudaGetLastError(), "k2_kernel");
 }
 
@@ -140,6 +142,7 @@ int launch_k3(agym_handle* h, const SimParams& p, const uint8_t* parts, const fl
               float* gamma, float* propensity, cudaStream_t s) {
   const long long NP = (long long)p.R * p.T * p.P;
   k3_kernel<<<unsigned((NP + 255) / 256), 256, 0, s>>>(p, parts, est, value, bid, gamma, propensity, NP);
+  h->launches += 1;
   return check_cuda(h, cudaGetLastError(), "k3_kernel");
 }
 
@@ -375,6 +378,7 @@ int launch_k4(agym_handle* h, const SimParams& p, const float* bid, const float*
                                                                  (const uint2*)parts, (uint32_t*)winner, (float4*)price,
                                                                  (float4*)second, (uint32_t*)outcome, N4, h->k4_scratch);
       k4_fold_kernel<<<unsigned((p.R * p.A + 255) / 256), 256, 0, s>>>(h->k4_scratch, p.acc, p.R * p.A);
+      h->launches += 2;
       return check_cuda(h, cudaGetLastError(), "k4_kernel_p2_acc");
     }
     k4_kernel_p2<<<unsigned((N4 + 255) / 256), 256, 0, s>>>(p, (const float4*)bid, (const float4*)true_ctr, (const float4*)value,
@@ -383,6 +387,7 @@ int launch_k4(agym_handle* h, const SimParams& p, const float* bid, const float*
   } else {
     k4_kernel_any<<<unsigned((N + 255) / 256), 256, 0, s>>>(p, bid, true_ctr, value, parts, winner, price, second, outcome, N, accumulate);
   }
+  h->launches += 1;
   return check_cuda(h, cudaGetLastError(), "k4_kernel");
 }
 

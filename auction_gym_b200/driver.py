@@ -185,7 +185,7 @@ def run_experiment(config_path, device=0, rank=0, world=1, precision=None, verbo
         auction, num_iter, rounds_per_iter, output_dir = instantiate_auction(
             rng, config, agents2items, agents2item_values, agents, max_slots, embedding_size, embedding_var, obs_embedding_size,
             num_runs=count, run_offset=first, device=device, precision=precision, seed=config["random_seed"],
-            rounds_capacity=config["rounds_per_iter"])
+            rounds_capacity=config["rounds_per_iter"], per_run_init=True)
         metrics, revenue = simulation_run(auction, num_iter, rounds_per_iter, verbose=verbose and rank == 0)
         auction.engine.close()
     metrics = gather_runs(metrics, world)

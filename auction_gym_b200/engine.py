@@ -106,6 +106,10 @@ class Engine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def launch_count(self):
+        """Kernels of libagym launched through this engine so far."""
+        return int(self.lib.agym_launch_count(self.handle))
+
     def set_option(self, name, value):
         """Kernel-selection override (include/agym.h: agym_set_option) -- tests and experiments only."""
         self._check(self.lib.agym_set_option(self.handle, name.encode(), float(value)))

@@ -3,23 +3,32 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[4]): runs sharded over the GPUs of one box,
-512 runs per GPU (4096 / 8, weak scaling), T = 10 000 rounds per iteration, A = 64 agents x I = 64 items,
-D = 5, Do = 4, P = 2, SecondPrice + TruthfulBidder + learnt Thompson-sampling allocator.
-One step = one iteration of every resident run = T rounds of the fused round-loop kernel (K1-K5) + the
-per-iteration allocator fits (K6, adam_ref: the reference's Adam + plateau scheduler + early-stop state
-machine) + the per-iteration metric read-out.  value = runs * T / step time (whole job, max over ranks).
+Workload (BASELINE.json configs[4]): 4096 runs sharded over the GPUs of one box (4096 / world
+each: STRONG scaling, the whole job is fixed), T = 10 000 rounds per iteration, A = 64 agents x I = 64 items, D = 5, Do = 4,
+P = 2, SecondPrice + TruthfulBidder + learnt Thompson-sampling allocator.  `--runs-per-gpu R` switches to weak scaling.
+One step = one iteration of every resident run = T rounds of the fused round-loop kernel (K1-K5) + the per-iteration
+allocator fits (K6, adam_ref: the reference's Adam + plateau scheduler + early-stop state machine) + the per-iteration
+metric read-out (+ at N > 1 the all-gather of the metric block, K8).  value = runs * T / step time (max over ranks).
+The timed steps are iterations W .. W+K-1 of ONE learning trajectory that starts from m ~ N(0, 1), q = 1: the fit gets
+cheaper as the allocators learn, so the iteration range is part of the configuration and is printed.
 
-The JSON line also carries: e2e (same step through the public API with the learnt state and metrics
-crossing PCIe from/to pinned host memory every step), roofline (dominant kernel) + roofline_kernels (every
-kernel, incl. the staged resolution kernel K4 the north star puts the HBM bar on), cpu_baseline (the oracle
-port timed on this box's host cores), clocks, gpu_launches.
+The JSON line also carries: e2e (same iterations through the public API with the learnt state and metrics crossing PCIe
+from / to pinned host memory every step), fit_epochs_mean, full_workload (the whole N = 100-iteration trajectory),
+roofline (dominant kernel) + roofline_kernels (every kernel, incl. the staged resolution kernel K4 the north star puts
+the HBM bar on), cpu_baseline, clocks, gpu_launches (counted by the library).
+
+`--impl reference` times the UNMODIFIED reference (oracle/_ref, a verbatim copy shipped by gpurun) on all host cores on
+the SAME iterations: each step fits the dumped fit inputs of iteration W + i of this trajectory
+(tests/golden/bench_fit_inputs.npz, written by tools/dump_bench_fit_inputs.py) and times the reference's round loop at the
+bench shape; fit_epochs_mean is printed by both arms.  The numpy port is timed beside it as a second, labelled number.
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -31,36 +40,72 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(A=64, I=64, D=5, Do=4, P=2, T=10000, runs_per_gpu=512)
+WORKLOAD = dict(A=64, I=64, D=5, Do=4, P=2, T=10000, runs_total=4096, iterations_full=100)
 METRIC = "auction opportunities/sec"
 UNIT = "opportunities/s"
+SEED = 0            # Philox seed of the round loop (per-run key = (SEED, global run index))
+INIT_SEED = 1000    # initial allocator state: m[r] ~ N(0, 1) from default_rng([INIT_SEED, global run index])
 
 
-def parse_args():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--runs-per-gpu", type=int, default=WORKLOAD["runs_per_gpu"])
+    ap.add_argument("--runs-total", type=int, default=WORKLOAD["runs_total"], help="strong scaling: runs of the whole job (default 4096)")
+    ap.add_argument("--runs-per-gpu", type=int, default=0, help="weak scaling: runs per GPU (overrides --runs-total)")
     ap.add_argument("--rounds", type=int, default=WORKLOAD["T"])
     ap.add_argument("--allocator", default="ts", choices=["ts", "oracle"], help="ts = SP_Truthful_TS shape (headline); oracle = SP_Oracle shape")
+    ap.add_argument("--fit-mode", default="adam_ref", choices=["adam_ref", "adam_fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary staged-kernel roofline measurements")
-    return ap.parse_args()
+    ap.add_argument("--no-aux", action="store_true", help="skip the staged-kernel roofline measurements and the shipped config")
+    ap.add_argument("--no-full", action="store_true", help="skip the whole-trajectory (100 iterations) measurement")
+    ap.add_argument("--full-iterations", type=int, default=WORKLOAD["iterations_full"])
+    return ap.parse_args(argv)
 
 
-def config_dict(args, world):
+def shard(args, world, rank):
+    """(first global run, runs on this rank, runs of the whole job, scaling)."""
+    if args.runs_per_gpu > 0:
+        return rank * args.runs_per_gpu, args.runs_per_gpu, args.runs_per_gpu * world, "weak"
+    base, extra = divmod(args.runs_total, world)
+    return rank * base + min(rank, extra), base + (1 if rank < extra else 0), args.runs_total, "strong"
+
+
+def config_dict(args, world, runs_job, scaling, first_it, n_it):
     w = WORKLOAD
-    return {"workload": f"synthetic SP_Truthful_TS shape: {args.runs_per_gpu * world} runs x {args.rounds} rounds/iteration x "
-                        f"{w['A']} agents x {w['I']} items, D={w['D']} Do={w['Do']} P={w['P']}, SecondPrice, TruthfulBidder, "
-                        f"{'learnt Thompson-sampling allocator + adam_ref fits' if args.allocator == 'ts' else 'OracleAllocator (no fits)'}",
-            "runs": args.runs_per_gpu * world, "runs_per_gpu": args.runs_per_gpu, "rounds_per_step": args.rounds,
+    return {"workload": f"synthetic SP_Truthful_TS shape: {runs_job} runs x {args.rounds} rounds/iteration x {w['A']} agents x {w['I']} items, "
+                        f"D={w['D']} Do={w['Do']} P={w['P']}, SecondPrice, TruthfulBidder, "
+                        f"{'learnt Thompson-sampling allocator + ' + args.fit_mode + ' fits' if args.allocator == 'ts' else 'OracleAllocator (no fits)'}; "
+                        f"timed steps = iterations {first_it}..{first_it + n_it - 1} of the learning trajectory from m ~ N(0,1), q = 1",
+            "runs": runs_job, "runs_per_gpu": runs_job // world, "rounds_per_step": args.rounds, "iterations": [first_it, first_it + n_it],
             "agents": w["A"], "items": w["I"], "embedding_size": w["D"], "obs_embedding_size": w["Do"],
-            "participants": w["P"], "allocation": "SecondPrice", "allocator": args.allocator, "fit_mode": "adam_ref",
-            "step": "one iteration: T rounds (fused K1-K5) + allocator fits (K6) + metric read-out",
-            "parallelism": f"runs sharded over {world} GPU(s), no data-path collective",
-            "l2": "no flush needed: per-step working set (learnt state + winner log + fit workspace, > 400 MB) exceeds the 126 MB L2"}
+            "participants": w["P"], "allocation": "SecondPrice", "allocator": args.allocator, "fit_mode": args.fit_mode,
+            "step": "one iteration: T rounds (fused K1-K5) + allocator fits (K6) + metric read-out" + (" + NCCL all-gather of the metric block (K8)" if world > 1 else ""),
+            "parallelism": f"runs sharded over {world} GPU(s) ({scaling} scaling), no data-path collective",
+            "l2": "no flush needed: per-step working set (learnt state + winner log + fit workspace, > 400 MB per 512 runs) exceeds the 126 MB L2"}
+
+
+def initial_m(first_run, count):
+    """Models.py:22 m ~ N(0, 1), one independent stream per GLOBAL run (the same run starts from the same state on any shard)."""
+    import torch
+
+    w = WORKLOAD
+    out = np.empty((count, w["A"], w["I"], w["Do"] + 1), np.float32)
+    for r in range(count):
+        out[r] = np.random.default_rng([INIT_SEED, first_run + r]).standard_normal(out.shape[1:], dtype=np.float32)
+    return torch.from_numpy(out)
+
+
+def make_engine(ag, _lib, R, T, learnt, device, run_offset):
+    from oracle import auction_oracle as ao  # catalog sampler only (main.py:60-72); never on the timed path
+
+    w = WORKLOAD
+    E, V = ao.make_catalog(np.random.default_rng(0), w["A"], w["I"], w["D"])  # shared by every run and rank
+    return ag.Engine(R=R, A=w["A"], I=w["I"], D=w["D"], Do=w["Do"], P=w["P"], mechanism=_lib.SECOND_PRICE, E=E, V=V, n_items=[w["I"]] * w["A"],
+                     alloc_kind=[_lib.ALLOC_TS if learnt else _lib.ALLOC_ORACLE] * w["A"], bidder_kind=[_lib.BID_TRUTHFUL] * w["A"],
+                     precision=_lib.FP32, device=device, run_offset=run_offset, rounds_capacity=T)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -120,40 +165,99 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profile_numbers(kernel_pattern, grid=None):
+    """Counters of the newest committed ncu summary (profiles/r*_ncu_full.txt, written by tools/ncu_summary.py) whose kernel
+    name matches; nothing here is a constant of this file.  `traffic` only when the capture's grid equals this run's."""
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full.txt"))):
+        block = {}
+        for ln in open(path):
+            if ln.startswith("Kernel Name"):
+                if block.get("name") and re.search(kernel_pattern, block["name"]):
+                    best = (path, block)
+                block = {"name": ln[len("Kernel Name"):].strip()}
+                continue
+            f = ln.split()
+            if len(f) >= 2 and not ln.startswith("-"):
+                try:
+                    block[f[0]] = float(f[1])
+                except ValueError:
+                    pass
+        if block.get("name") and re.search(kernel_pattern, block["name"]):
+            best = (path, block)
+    if best is None:
+        return None
+    path, b = best
+    out = {"source": os.path.relpath(path, ROOT), "kernel": b["name"],
+           "warp_instructions_per_sm_cycle": b.get("sm__inst_executed.avg.per_cycle_elapsed"),
+           "issue_slots_active_pct": b.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+           "warps_active_pct": b.get("sm__warps_active.avg.pct_of_peak_sustained_active"),
+           "registers_per_thread": b.get("launch__registers_per_thread"), "grid": b.get("launch__grid_size"),
+           "dram_bytes": (b.get("dram__bytes_read.sum", 0.0) + b.get("dram__bytes_write.sum", 0.0)) * 1e6}
+    out["traffic_matches_this_grid"] = bool(grid is not None and out["grid"] == grid)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
+def cpu_kind():
+    from oracle import ref_bench
+
+    return "reference" if ref_bench.reference_available() else "port"
+
+
 def run_reference_arm(args, rank, world):
-    """CPU arm: the oracle port on all host cores (the Python reference cannot travel to the GPU box)."""
+    """CPU arm (rank 0 only): the unmodified reference on all host cores, on the SAME iterations as the GPU arm."""
     if rank != 0:
         return
-    from oracle import cpu_bench
+    from oracle import ref_bench
 
     w = WORKLOAD
-    cores = os.cpu_count() or 1
-    workers = max(1, cores)
-    per_step = []
+    learnt = args.allocator == "ts"
+    kind = cpu_kind()
+    workers = max(1, min(os.cpu_count() or 1, 64))
+    _, _, runs_job, scaling = shard(args, world, 0)
+    fits_per_worker = max(1, 16 // workers) if learnt else 0  # >= 16 fits per step: the mean epoch count over K = 20 steps is good to ~2 %
+    n_rounds = 400
     t_all = time.perf_counter()
-    for i in range(args.warmup + args.steps):
-        warm = i < args.warmup
-        r = cpu_bench.run(w["A"], w["I"], w["D"], w["Do"], w["P"], args.rounds, n_rounds=200 if warm else 600, n_fits=0 if warm else 1,
-                          workers=workers, seed=i)
-        if not warm:
-            per_step.append(r)
-    agg = float(np.mean([r["aggregate_opp_per_s"] for r in per_step]))
-    if args.allocator == "oracle":
-        agg = float(np.mean([r["round_only_per_core"] for r in per_step])) * workers
-    sample = (f"per step and per core: 600 rounds of the scalar port (oracle/auction_oracle.simulate_rounds_scalar) + 1 allocator fit "
-              f"(oracle/fit_oracle) at the bench shape, {workers} processes; opportunities/s = T / (T / round_rate + A * fit_seconds) "
-              f"summed over cores (runs are independent)")
-    line = {"impl": "reference", "metric": METRIC, "value": agg, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * float(np.mean([r["wall_seconds"] for r in per_step])), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32/f64 (numpy port of the reference's mix)", "data": "synthetic",
-            "config": config_dict(args, world),
-            "cpu_baseline": {"value": agg, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
-                             "per_core": float(np.mean([r["per_core_opp_per_s"] for r in per_step])),
-                             "round_loop_only_per_core": float(np.mean([r["round_only_per_core"] for r in per_step])),
-                             "fit_seconds": float(np.mean([r["fit_seconds"] for r in per_step])),
-                             "fit_epochs": float(np.mean([r["fit_epochs"] for r in per_step]))},
-            "e2e": {"value": agg, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    rows, ports = [], []
+    with ref_bench.make_pool(workers) as pool:
+        for i in range(args.warmup + args.steps):
+            warm = i < args.warmup
+            r = ref_bench.run(kind, w["A"], w["I"], w["D"], w["Do"], w["P"], args.rounds, iteration=i, n_rounds=100 if warm else n_rounds,
+                              fits_per_worker=0 if warm else fits_per_worker, workers=workers, learnt=learnt, seed=i, pool=pool)
+            if not warm:
+                rows.append(r)
+                if kind == "reference":  # the numpy port on the same fits, as a second, labelled number
+                    ports.append(ref_bench.run("port", w["A"], w["I"], w["D"], w["Do"], w["P"], args.rounds, iteration=i, n_rounds=n_rounds,
+                                               fits_per_worker=fits_per_worker, workers=workers, learnt=learnt, seed=i, pool=pool))
+
+    def agg(rs):
+        if learnt:
+            return float(np.mean([r["aggregate_opp_per_s"] for r in rs]))
+        return float(np.mean([r["round_only_per_core"] for r in rs])) * workers
+
+    value = agg(rows)
+    sample = (f"per step i (iteration {args.warmup} + i of the GPU arm's trajectory) and per core: {n_rounds} rounds of the {'unmodified reference' if kind == 'reference' else 'numpy port'}'s "
+              f"simulate_opportunity at the bench shape + {fits_per_worker} allocator fit(s) on the dumped inputs of that iteration "
+              f"(tests/golden/bench_fit_inputs.npz); {workers} processes, one torch thread each; opportunities/s = T / (T / round_rate + A * fit_seconds) summed over cores")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(np.mean([r["wall_seconds"] for r in rows])), "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f32/f64 (the reference's own mix)", "data": "synthetic",
+            "config": config_dict(args, world, runs_job, scaling, args.warmup, args.steps),
+            "fit_epochs_mean": float(np.mean([r["fit_epochs_mean"] for r in rows])) if learnt else None,
+            "fit_epochs_per_step": [r["fit_epochs_mean"] for r in rows] if learnt else None,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample,
+                             "per_core": value / workers,
+                             "round_loop_only_per_core": float(np.mean([r["round_only_per_core"] for r in rows])),
+                             "fit_seconds": float(np.mean([r["fit_seconds_mean"] for r in rows])),
+                             "fit_epochs": float(np.mean([r["fit_epochs_mean"] for r in rows])),
+                             "fits_timed": int(sum(r["fits_timed"] for r in rows))},
+            "port": ({"value": agg(ports), "unit": UNIT, "kind": "port", "cores": workers,
+                      "round_loop_only_per_core": float(np.mean([r["round_only_per_core"] for r in ports])),
+                      "fit_seconds": float(np.mean([r["fit_seconds_mean"] for r in ports])),
+                      "fit_epochs": float(np.mean([r["fit_epochs_mean"] for r in ports])),
+                      "note": "oracle/auction_oracle.py + oracle/fit_oracle.py (the numpy restatement) on the same sample"} if ports else None),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "total_seconds": time.perf_counter() - t_all}
     print(json.dumps(line), flush=True)
 
@@ -173,7 +277,6 @@ def main():
 
     import auction_gym_b200 as ag
     from auction_gym_b200 import _lib
-    from oracle import auction_oracle as ao  # catalog sampler only (main.py:60-72); never on the timed path
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -183,62 +286,70 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     w = WORKLOAD
-    A, I, D, Do, P, T, R = w["A"], w["I"], w["D"], w["Do"], w["P"], args.rounds, args.runs_per_gpu
+    A, I, D, Do, P, T = w["A"], w["I"], w["D"], w["Do"], w["P"], args.rounds
+    first_run, R, runs_job, scaling = shard(args, world, rank)
     K = Do + 1
     learnt = args.allocator == "ts"
-    cat_rng = np.random.default_rng(0)  # the catalog is shared by every run and rank (main.py:60-72)
-    E, V = ao.make_catalog(cat_rng, A, I, D)
-    eng = ag.Engine(R=R, A=A, I=I, D=D, Do=Do, P=P, mechanism=_lib.SECOND_PRICE, E=E, V=V, n_items=[I] * A,
-                    alloc_kind=[_lib.ALLOC_TS if learnt else _lib.ALLOC_ORACLE] * A, bidder_kind=[_lib.BID_TRUTHFUL] * A,
-                    precision=_lib.FP32, device=local_rank, run_offset=rank * R, rounds_capacity=T)
-    g = torch.Generator(device="cpu").manual_seed(1000 + rank)
+    fit_mode = _lib.FIT_ADAM_FAST if args.fit_mode == "adam_fast" else _lib.FIT_ADAM_REF
+    eng = make_engine(ag, _lib, R, T, learnt, local_rank, first_run)
     if learnt:
-        m_host = torch.randn((R, A, I, K), generator=g).pin_memory()      # Models.py:22  m ~ N(0, 1)
+        m0_host = initial_m(first_run, R)
+        m_host = m0_host.clone().pin_memory()
         q_host = torch.ones((R, A, I, K)).pin_memory()
-        mp_host = m_host.clone().pin_memory()
-        m0_host = m_host.clone()
+        mp_host = m0_host.clone().pin_memory()
         eng.set_allocator_state(m_host, q_host, mp_host)
     acc_host = torch.empty((R, A, _lib.NUM_METRICS), dtype=torch.float64).pin_memory()
     rev_host = torch.empty((R,), dtype=torch.float64).pin_memory()
-    seed = 0
+    # K8: every iteration's metric block of every rank (main.py:186-222 keeps per-run rows, so gather, not reduce)
+    gathered = torch.empty((world, R, A * _lib.NUM_METRICS + 1), dtype=torch.float64, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream(dev)
     ev_pairs = {"rounds": [], "fit": []}
+    epochs_sum = torch.zeros(2, dtype=torch.float64, device=dev)  # {sum of epochs, fits} over the steps that ask for it
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local_rank])
 
-    def step_device(it, timed):
-        """One iteration with everything resident in HBM; the metric block is read back (1.5 MB) at the end."""
+    def read_out():
+        """Per-iteration metric read-out: D2H of this rank's block; at N > 1 also the NCCL all-gather (K8)."""
+        if world > 1:
+            blk = torch.cat([eng.acc.reshape(R, -1), eng.revenue.reshape(R, 1)], dim=1)
+            dist.all_gather_into_tensor(gathered.view(world * R, -1), blk)
+        acc_host.copy_(eng.acc, non_blocking=True)
+        rev_host.copy_(eng.revenue, non_blocking=True)
+
+    def step_device(it, timed, count_epochs=False):
+        """One iteration with everything resident in HBM."""
         eng.clear_iteration()
         if timed:
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record(stream)
-        eng.simulate(seed, it, T)
+        eng.simulate(SEED, it, T)
         if timed:
             e1.record(stream)
         if learnt:
-            eng.update_allocators(want_info=False)
+            info = eng.update_allocators(want_info=count_epochs, fit_mode=fit_mode)
+            if count_epochs:
+                ran = info[..., 1]
+                epochs_sum.add_(torch.stack([ran.sum(dtype=torch.float64), (ran > 0).sum().to(torch.float64)]))
         if timed:
             e2.record(stream)
             ev_pairs["rounds"].append((e0, e1))
             ev_pairs["fit"].append((e1, e2))
-        acc_host.copy_(eng.acc, non_blocking=True)
-        rev_host.copy_(eng.revenue, non_blocking=True)
+        read_out()
 
     def step_e2e(it):
         """The same iteration through the public API with HOST buffers: learnt state up, metrics + state down."""
         if learnt:
             eng.set_allocator_state(m_host, q_host, mp_host, non_blocking=True)
         eng.clear_iteration()
-        eng.simulate(seed, it, T)
+        eng.simulate(SEED, it, T)
         if learnt:
-            eng.update_allocators(want_info=False)
+            eng.update_allocators(want_info=False, fit_mode=fit_mode)
             m_host.copy_(eng.m, non_blocking=True)
             q_host.copy_(eng.q, non_blocking=True)
             mp_host.copy_(eng.m_prev, non_blocking=True)
-        acc_host.copy_(eng.acc, non_blocking=True)
-        rev_host.copy_(eng.revenue, non_blocking=True)
+        read_out()
         stream.synchronize()
 
     def timed_region(fn, steps, it0):
@@ -256,26 +367,32 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- warm-up, then the device-resident timed region ----
-    it = 0
-    for _ in range(args.warmup):
+    def reset_state():
+        if learnt:
+            m_host.copy_(m0_host); q_host.fill_(1.0); mp_host.copy_(m0_host)
+            eng.set_allocator_state(m_host, q_host, mp_host)
+
+    # ---- warm-up, then the device-resident timed region: iterations W .. W+K-1 ----
+    for it in range(args.warmup):
         step_device(it, False)
-        it += 1
     torch.cuda.synchronize(dev)
     clocks = ClockSampler(local_rank)
     clocks.start()
-    ms_total = timed_region(lambda i: step_device(i, True), args.steps, it)
+    launches0 = eng.launch_count()
+    ms_total = timed_region(lambda i: step_device(i, True, count_epochs=True), args.steps, args.warmup)
+    launches = eng.launch_count() - launches0
     clk = clocks.stop()
-    it += args.steps
-    opp_per_step = R * T * world
+    opp_per_step = runs_job * T
     value = opp_per_step * args.steps / (ms_total * 1e-3)
     k_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) if v else 0.0 for k, v in ev_pairs.items()}
+    per_step_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in ev_pairs.items()}
+    es = epochs_sum.clone()
+    if world > 1:
+        dist.all_reduce(es)
+    fit_epochs_mean = float(es[0] / es[1]) if learnt and float(es[1]) > 0 else None
 
     # ---- end to end through host buffers: the SAME iterations of the same learning trajectory ----
-    # (the fit gets cheaper as the allocators learn -- fewer epochs, fewer distinct items per agent -- so both regions restart
-    # from the initial host state and time iterations W .. W + K - 1 with the same Philox counters)
-    if learnt:
-        m_host.copy_(m0_host); q_host.fill_(1.0); mp_host.copy_(m0_host)
+    reset_state()
     for i in range(args.warmup):
         step_e2e(i)
     ms_e2e = timed_region(step_e2e, args.steps, args.warmup)
@@ -283,6 +400,49 @@ def main():
     state_bytes = 3 * R * A * I * K * 4 if learnt else 0
     h2d = state_bytes
     d2h = state_bytes + R * A * _lib.NUM_METRICS * 8 + R * 8
+
+    # ---- the whole trajectory: N = 100 iterations from the initial state ----
+    full = None
+    if not args.no_full:
+        reset_state()
+        n_full = args.full_iterations
+        per_it = []
+        info_keep = []
+        barrier()
+        torch.cuda.synchronize(dev)
+        s_all, e_all = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_all.record(stream)
+        for it in range(n_full):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            eng.clear_iteration()
+            eng.simulate(SEED, it, T)
+            if learnt:
+                info = eng.update_allocators(want_info=True, fit_mode=fit_mode)
+                ran = info[..., 1]
+                info_keep.append(torch.stack([ran.sum(dtype=torch.float64), (ran > 0).sum().to(torch.float64)]))
+            read_out()
+            b.record(stream)
+            per_it.append((a, b))
+        e_all.record(stream)
+        torch.cuda.synchronize(dev)
+        barrier()
+        ms_full = torch.tensor([s_all.elapsed_time(e_all)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms_full, op=dist.ReduceOp.MAX)
+        ms_full = float(ms_full.item())
+        ep = None
+        if learnt:
+            ep_t = torch.stack(info_keep)
+            if world > 1:
+                dist.all_reduce(ep_t)
+            ep = [float(x[0] / max(float(x[1]), 1.0)) for x in ep_t.cpu()]
+        full = {"iterations": n_full, "opportunities": runs_job * T * n_full, "seconds": ms_full * 1e-3,
+                "value": runs_job * T * n_full / (ms_full * 1e-3), "unit": UNIT,
+                "ms_per_iteration": [round(a.elapsed_time(b), 3) for a, b in per_it],
+                "fit_epochs_mean_per_iteration": [round(x, 1) for x in ep] if ep else None,
+                "target": {"value": 1e9, "n_gpus": 8, "source": "BASELINE.json north_star"},
+                "note": "whole job, max over ranks, device-resident state, per-iteration metric read-out (and all-gather at N > 1) included"}
 
     # ---- roofline bookkeeping ----
     peak, peak_src = measured_peaks()
@@ -297,73 +457,81 @@ def main():
                                                 # production mode draws the Thompson noise in logit space: one normal per (participant, item)
                                                 "normals_per_s": (R * T * P * I / k_ms["rounds"] * 1e3) if learnt else 0.0,
                                                 "sigmoids_per_s": R * T * P * (2 * I + 1) / k_ms["rounds"] * 1e3,
-                                                "bound": "issue (exp, FMA, Philox + Box-Muller) and L1/L2 reads of the learnt state; HBM traffic is the 20 B/opportunity winner record"}
+                                                "bound": "issue (exp, FMA, Philox + Box-Muller) and L1/L2 reads of the learnt state; HBM traffic is the 20 B/opportunity winner record",
+                                                "from_profile": profile_numbers(r"sim_kernel", None)}
     if learnt and k_ms["fit"] > 0:
-        kernels["bucket_kernel + fit_kernel (K6)"] = {"ms": k_ms["fit"], "share": k_ms["fit"] / (ms_total / args.steps),
-                                                       "algorithmic_bytes": bytes_fit, "achieved_gbs": bytes_fit / k_ms["fit"] / 1e6,
-                                                       "fits_per_s": R * A / k_ms["fit"] * 1e3, "rows_per_fit": rows_per_fit,
-                                                       "bound": "instruction issue: ~8 000 sequential Adam epochs per fit on register / shared-memory resident state"}
+        fit_epochs_total = float(es[0]) / max(world, 1)
+        kernels["fit kernels (K6)"] = {"ms": k_ms["fit"], "share": k_ms["fit"] / (ms_total / args.steps), "ms_per_step": per_step_ms["fit"],
+                                       "algorithmic_bytes": bytes_fit, "achieved_gbs": bytes_fit / k_ms["fit"] / 1e6,
+                                       "fits_per_s": R * A / k_ms["fit"] * 1e3, "rows_per_fit": rows_per_fit,
+                                       "fit_epochs_per_s": fit_epochs_total / (k_ms["fit"] * args.steps) * 1e3,
+                                       "bound": "instruction issue: thousands of sequential Adam epochs per fit on register / shared-memory resident state",
+                                       "from_profile": profile_numbers(r"fit_warp_kernel<3", R * A)}
     aux = {}
     if not args.no_aux:
         # staged resolution kernel K4(+K5) on the same opportunities: HBM-bound, 13P+10 = 36 B/opportunity
-        eng.clear_iteration()
-        b = eng.staged_round(seed, 0, T)
+        Rk = min(R, 512)
+        engk = eng if Rk == R else make_engine(ag, _lib, Rk, T, learnt, local_rank, first_run)
+        if engk is not eng and learnt:
+            engk.set_allocator_state(m0_host[:Rk])
+        engk.clear_iteration()
+        b = engk.staged_round(SEED, 0, T)
         flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # 4x the 126 MB L2
         for accumulate in (False, True):
             for _ in range(3):
-                eng.k4_resolve(seed, 0, T, b, accumulate)
+                engk.k4_resolve(SEED, 0, T, b, accumulate)
             torch.cuda.synchronize(dev)
             ts = []
             for _ in range(10):
                 flush.fill_(1)  # evict K4's inputs from L2 so every timed launch reads HBM
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record(stream); eng.k4_resolve(seed, 0, T, b, accumulate); e.record(stream)
+                s.record(stream); engk.k4_resolve(SEED, 0, T, b, accumulate); e.record(stream)
                 torch.cuda.synchronize(dev)
                 ts.append(s.elapsed_time(e))
             ms4 = float(np.mean(ts))
-            by = R * T * (13 * P + 10)
+            by = Rk * T * (13 * P + 10)
+            prof = profile_numbers(r"k4_kernel_p2_acc" if accumulate else r"k4_kernel_p2\b", None)
             aux["k4_resolve" + ("+accumulate" if accumulate else "")] = {
                 "bound": "hbm", "achieved": by / ms4 / 1e6, "peak": peak, "unit": "GB/s", "frac": by / ms4 / 1e6 / peak,
-                "ms": ms4, "algorithmic_bytes": by, "opportunities_per_s": R * T / ms4 * 1e3, "traffic": None,
-                "note": f"{R * T} opportunities, {by / 1e6:.0f} MB algorithmic; L2 flushed (512 MB fill) before every timed launch; outside the timed step"}
+                "ms": ms4, "algorithmic_bytes": by, "opportunities_per_s": Rk * T / ms4 * 1e3,
+                "traffic": prof["dram_bytes"] if prof else None, "from_profile": prof,
+                "note": f"{Rk * T} opportunities, {by / 1e6:.0f} MB algorithmic; L2 flushed (512 MB fill) before every timed launch; outside the timed step"}
         del b, flush
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures of exactly this
-    # shape (profiles/r1_fit_warp_ncu_full.txt, profiles/r1_sim_kernel_g8_ncu_full.txt, profiles/r1_sim_kernel_k4_ncu_full.txt); null for any other shape
-    std_shape = R == WORKLOAD["runs_per_gpu"] and T == WORKLOAD["T"] and learnt
-    ncu_traffic = {"sim_kernel (fused K1-K5)": 87358464 + 63195904, "bucket_kernel + fit_kernel (K6)": 250489600 + 71059200,
-                   "k4_resolve+accumulate": 141547520 + 49876736} if std_shape else {}
-    for k, v in {**kernels, **aux}.items():
-        v["traffic"] = ncu_traffic.get(k)
+        if engk is not eng:
+            engk.close()
     dominant = max(kernels.items(), key=lambda kv: kv[1]["ms"])
+    dprof = dominant[1].get("from_profile")
     roofline = {"kernel": dominant[0], "bound": "hbm", "achieved": dominant[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dominant[1]["achieved_gbs"] / peak, "traffic": ncu_traffic.get(dominant[0]), "peak_source": peak_src,
-                # what actually bounds it (same ncu capture): warp instructions issued per SM cycle against the 4 schedulers
-                "issue": {"achieved": 2.73, "peak": 4.0, "unit": "warp instructions / SM cycle", "frac": 0.68,
-                          "issue_slots_active": 0.73, "warp_instructions_per_fit_epoch": 943, "source": "profiles/r1_fit_warp_ncu_full.txt"} if std_shape else None,
+                "frac": dominant[1]["achieved_gbs"] / peak,
+                "traffic": dprof["dram_bytes"] if dprof and dprof.get("traffic_matches_this_grid") else None, "peak_source": peak_src,
+                "from_profile": dprof,
                 "note": "the dominant kernel is not HBM-bound (" + dominant[1]["bound"] + "); its algorithmic HBM bytes are tiny by design. "
                         "The HBM-bound kernel of the path is the staged resolution kernel: see roofline_kernels.k4_resolve"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import cpu_bench
+        from oracle import ref_bench
 
-        r = cpu_bench.run(A, I, D, Do, P, T, n_rounds=3000, n_fits=6 if learnt else 0, workers=1)
-        cpu_val = r["per_core_opp_per_s"] if learnt else r["round_only_per_core"]
-        cpu = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"3000 rounds of oracle.auction_oracle.simulate_rounds_scalar + {6 if learnt else 0} allocator fits (oracle.fit_oracle, "
-                         f"mean {r['fit_epochs']:.0f} epochs, {r['fit_seconds']:.2f} s each) at the bench shape on one core; "
-                         f"value = T / (T / round_rate + A * fit_seconds)",
-               "round_loop_only": r["round_only_per_core"], "host_cores": os.cpu_count(),
-               "ideal_all_cores": cpu_val * (os.cpu_count() or 1)}
+        kind = cpu_kind()
+        # a bounded sample (about 20 s on one core) spread over the timed iterations: 4 fits of 4 iterations + 500 rounds
+        its = sorted({args.warmup + int(round(f * (args.steps - 1))) for f in (0.0, 0.33, 0.67, 1.0)})
+        rs = [ref_bench.run(kind, A, I, D, Do, P, T, iteration=i, n_rounds=500 // len(its), fits_per_worker=1 if learnt else 0, workers=1, learnt=learnt, seed=i)
+              for i in its]
+        round_rate = float(np.mean([r["round_only_per_core"] for r in rs]))
+        fit_s = float(np.mean([r["fit_seconds_mean"] for r in rs]))
+        cpu_val = T / (T / round_rate + A * fit_s) if learnt else round_rate
+        cpu = {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"iterations {its} of this trajectory: {500 // len(its)} rounds of simulate_opportunity at the bench shape + 1 allocator fit on the dumped inputs "
+                         f"(tests/golden/bench_fit_inputs.npz) each, one core, one torch thread; value = T / (T / round_rate + A * fit_seconds)",
+               "round_loop_only": round_rate, "fit_seconds": fit_s, "fit_epochs": float(np.mean([r["fit_epochs_mean"] for r in rs])),
+               "host_cores": os.cpu_count(), "ideal_all_cores": cpu_val * (os.cpu_count() or 1)}
 
     shipped = None
     if rank == 0 and world == 1 and not args.no_aux:
         # BASELINE.json configs[1] through the reference-facing driver (parse_config -> Auction / Agent -> five CSV tables'
         # worth of metrics): 3 runs x 20 iterations x 10 000 rounds, 6 agents x 12 items, 360 allocator fits.  Wall clock,
         # everything included (engine construction, catalog upload, fits, per-iteration metric read-out); second of two runs.
-        import auction_gym_b200 as ag
-
-        cfg_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "config", "SP_Truthful_TS.json")
+        cfg_path = os.path.join(ROOT, "config", "SP_Truthful_TS.json")
         walls = []
         for _ in range(2):
             torch.cuda.synchronize(dev)
@@ -374,17 +542,20 @@ def main():
         c = res["config"]
         n_opp = int(c.get("num_runs", res["metrics"].shape[0])) * c["num_iter"] * c["rounds_per_iter"]
         shipped = {"config": "config/SP_Truthful_TS.json", "opportunities": n_opp, "wall_s": walls[-1], "value": n_opp / walls[-1], "unit": UNIT,
-                   "reference_published": {"wall_s": 1201, "value": 500, "where": "BASELINE.md: python src/main.py config/SP_Truthful_TS.json on 8 host cores"}}
+                   "reference_surveyed": {"wall_s": 1201, "value": 500, "where": "BASELINE.md section 2: python src/main.py config/SP_Truthful_TS.json on 8 host cores (surveyor-measured, not published)"}}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": config_dict(args, world),
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config_dict(args, world, runs_job, scaling, args.warmup, args.steps),
+                "fit_epochs_mean": fit_epochs_mean,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                         "note": "same iterations of the same trajectory as `value` (restart from the initial host state, same warm-up); every step "
                                 "uploads the learnt state from pinned host memory and reads state + metrics back"},
-                "gpu_launches": args.steps * (4 if learnt else 1),  # sim_kernel + bucket_kernel + fit_order_kernel + fit_warp_kernel per step
-                "round_loop": {"value": R * T * world / k_ms["rounds"] * 1e3 if k_ms["rounds"] else None, "unit": UNIT, "ms": k_ms["rounds"]},
+                "gpu_launches": int(launches), "gpu_launches_note": "agym_launch_count difference over the timed region on rank 0 (sim_kernel, bucket_kernel, "
+                                                                     "fit_classify_kernel, fit_order_kernel, two fit_warp_kernel instantiations per step)",
+                "round_loop": {"value": runs_job * T / k_ms["rounds"] * 1e3 if k_ms["rounds"] else None, "unit": UNIT, "ms": k_ms["rounds"]},
+                "full_workload": full,
                 "roofline": roofline, "roofline_kernels": {**kernels, **aux}, "cpu_baseline": cpu, "shipped_config": shipped, "clocks": clk}
         print(json.dumps(line), flush=True)
     eng.close()

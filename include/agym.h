@@ -191,6 +191,10 @@ int64_t agym_retained_capacity(const agym_handle* h);
  * Net / gross utility and revenue are NOT touched (Agent.clear_utility and Auction.clear_revenue are separate calls). */
 int agym_retain_logs(agym_handle* h, void* stream);
 
+/* Number of kernels of this library launched through this handle so far (bench.py's gpu_launches is a difference of
+ * two readings; the reference has no counterpart: it launches nothing). */
+uint64_t agym_launch_count(const agym_handle* h);
+
 /* Kernel-selection overrides for tests and experiments (the library never reads the environment): "fit_warp" 0 = CTA
  * fit kernels only, "fit_dense" 0/1, "fit_nt" threads per CTA, "fit_ncap" rows staged per fit as a multiple of the mean,
  * "fit_heavy" whole-warp threshold of the CTA kernel, "sim_g" lane-group width of the round loop (8, 16, 32),

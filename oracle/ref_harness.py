@@ -1,10 +1,11 @@
 """TEST INFRASTRUCTURE ONLY -- harness that drives the UNMODIFIED reference in replay mode.
 
 This file is part of ``oracle/`` (the checker).  Nothing in the product path
-(``auction_gym_b200/``) may import it.  It is only usable in the build container,
-where the reference tree is mounted read-only at ``/root/reference``; the GPU box
-has no such tree, so everything that runs there uses the committed fixtures in
-``tests/golden/`` that ``oracle/make_golden.py`` produced with this harness.
+(``auction_gym_b200/``) may import it.  The reference tree it drives is
+``oracle/_ref/src`` (the verbatim, git-ignored copy written by ``oracle/make_ref.py``,
+which travels to the GPU box) or ``/root/reference/src`` (build container only).  The
+``-m gpu`` tests never need it: they use the committed fixtures in ``tests/golden/``
+that ``oracle/make_golden.py`` produced with this harness.
 
 What it does:
   * stubs ``matplotlib`` / ``seaborn`` (not installed) and lets
@@ -30,7 +31,9 @@ from unittest import mock
 
 import numpy as np
 
-REF_SRC = os.environ.get("AGYM_REF_SRC", "/root/reference/src")
+from . import make_ref as _make_ref
+
+REF_SRC = os.environ.get("AGYM_REF_SRC") or _make_ref.ref_src() or "/root/reference/src"
 REF_CONFIG = os.path.join(os.path.dirname(REF_SRC), "config")
 
 _ref_modules = None

@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "agym.h")
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"^\s*(?:const\s+char\*|int64_t|size_t|int)\s+(agym_\w+)\s*\(", src, flags=re.M)))
+    return sorted(set(re.findall(r"^\s*(?:const\s+char\*|int64_t|uint64_t|size_t|int)\s+(agym_\w+)\s*\(", src, flags=re.M)))
 
 
 def test_header_declares_the_documented_entry_points():

@@ -16,13 +16,13 @@ def test_bench_line_carries_the_contract_keys():
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3", "--runs-per-gpu", "16", "--rounds", "2000",
-                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+                          "--no-cpu-baseline", "--full-iterations", "4"], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
-              "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+              "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "fit_epochs_mean", "full_workload"):
         assert k in d, k
     assert d["metric"] == "auction opportunities/sec" and d["unit"] == "opportunities/s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3
     assert d["scaling"] == "weak" and d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
@@ -31,7 +31,11 @@ def test_bench_line_carries_the_contract_keys():
     assert abs(d["value"] - opp / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
     e = d["e2e"]
     assert e["unit"] == d["unit"] and 0 < e["value"] <= d["value"] * 1.05 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
-    assert d["gpu_launches"] == 2 * 4
+    assert d["gpu_launches"] == 2 * 6  # sim_kernel, bucket_kernel, fit_classify_kernel, fit_order_kernel, fit_warp_kernel x 2 per step
+    assert d["config"]["iterations"] == [3, 5] and d["fit_epochs_mean"] > 1000
+    f = d["full_workload"]
+    assert f["iterations"] == 4 and len(f["ms_per_iteration"]) == 4 and len(f["fit_epochs_mean_per_iteration"]) == 4
+    assert abs(f["value"] - 16 * 2000 * 4 / f["seconds"]) <= 1e-6 * f["value"]
     r = d["roofline"]
     assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     k4 = d["roofline_kernels"]["k4_resolve"]

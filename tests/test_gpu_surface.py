@@ -189,3 +189,19 @@ def test_first_price_value_learning_config_learns_to_shade(tmp_path):
     assert gamma[1] < 0.97 and gamma[2] < 0.97, gamma   # afterwards: searched gammas in [0.1, 1]
     assert surplus[1] > surplus[0] and revenue[1] < revenue[0], (surplus, revenue)
     assert np.isfinite(m).all()
+
+
+@pytest.mark.parametrize("cfg", ["FP_DR_TS", "SP_Truthful_TS"])
+def test_shards_reproduce_the_single_device_job(tmp_path, cfg, monkeypatch):
+    """The same seed gives the same per-run metrics whichever rank owns a run (world = 1, 2 and num_runs): the Philox key AND
+    every initial model draw (allocator m, win-rate and policy weights) are keyed by the global run index."""
+    _need_gpu()
+    from auction_gym_b200 import driver
+
+    path = _small_config(tmp_path, cfg, num_runs=4, num_iter=2, rounds_per_iter=400)
+    monkeypatch.setattr(driver, "gather_runs", lambda local, world: local)  # no process group here: shards are compared directly
+    whole = driver.run_experiment(path, rank=0, world=1)
+    for world in (2, 4):
+        parts = [driver.run_experiment(path, rank=r, world=world) for r in range(world)]
+        np.testing.assert_array_equal(np.concatenate([p["metrics"] for p in parts]), whole["metrics"], err_msg=f"{cfg} world {world}")
+        np.testing.assert_array_equal(np.concatenate([p["revenue"] for p in parts]), whole["revenue"], err_msg=f"{cfg} world {world}")

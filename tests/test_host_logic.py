@@ -143,8 +143,9 @@ def test_philox_restatement_known_answers():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the CPU arm: the oracle port on the host cores) needs no GPU; its single JSON line must
-    carry the keys the driver reads, on the same metric / unit / workload as the GPU arm."""
+    """`bench.py --impl reference` (the CPU arm: the unmodified reference from oracle/_ref on the host cores, or the numpy port
+    when that copy is absent) needs no GPU; its single JSON line must carry the keys the driver reads, on the same metric /
+    unit / workload / iterations as the GPU arm."""
     import json
     import subprocess
     import sys
@@ -157,8 +158,15 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "auction opportunities/sec" and d["unit"] == "opportunities/s"
-    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["n_gpus"] == 1
+    assert d["higher_is_better"] is True and d["scaling"] == "strong" and d["vs_baseline"] is None and d["n_gpus"] == 1
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    have_ref = os.path.isfile(os.path.join(root, "oracle", "_ref", "src", "Auction.py")) or os.path.isfile("/root/reference/src/Auction.py")
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["iterations"] == [0, 1] and d["config"]["runs"] == 4096
+    # iteration 0 of the trajectory: m ~ N(0, 1), q = 1 -- the long fits (the GPU arm's fit_epochs_mean of iteration 0 is ~8 100)
+    assert 5000 < d["fit_epochs_mean"] < 12000 and d["cpu_baseline"]["fits_timed"] >= 8
+    if have_ref:
+        assert d["port"]["kind"] == "port" and abs(d["port"]["fit_epochs"] / d["fit_epochs_mean"] - 1) < 0.05
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
