@@ -374,8 +374,9 @@ def main():
 
     # ---- warm-up, then the device-resident timed region: iterations W .. W+K-1 ----
     for it in range(args.warmup):
-        step_device(it, False)
+        step_device(it, False, count_epochs=True)  # same code path as the timed steps (no first-call costs inside the timed region)
     torch.cuda.synchronize(dev)
+    epochs_sum.zero_()
     clocks = ClockSampler(local_rank)
     clocks.start()
     launches0 = eng.launch_count()
