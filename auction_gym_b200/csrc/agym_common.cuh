@@ -200,7 +200,8 @@ struct agym_handle {
   double* d_adam_sz0 = nullptr;  // [kAdamTable] 2e-3 / (1 - 0.9^t), t = epoch + 1 (torch Adam step size at lr 2e-3)
   float* d_adam_bc2s = nullptr;  // [kAdamTable] sqrt(1 - 0.999^t)
   float2* d_adam_ep = nullptr;   // [kAdamTable] {float(d_adam_sz0), d_adam_bc2s}: one 64-bit load per epoch
-  float* k4_scratch = nullptr;   // [R][A][8 buckets][8] float partial sums of the staged resolution kernel (lazy)  // [kAdamTable] sqrt(1 - 0.999^t)
+  float* k4_scratch = nullptr;   // [R][chunks][A * 5 + 1] float partial sums of the staged resolution kernel (lazy)
+  size_t k4_scratch_bytes = 0;
   bool agents_set = false, catalog_set = false;
   bool any_learnt = false, any_shaded = false;
   int max_items = 0;

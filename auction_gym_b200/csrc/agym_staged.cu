@@ -236,86 +236,144 @@ __global__ void __launch_bounds__(256) k4_kernel_p2(const SimParams p, const flo
 }
 
 // P == 2 with accumulation (K4 + K5): the same resolution, plus charge / set_price bookkeeping (Agent.py:70-77,
-// 104-112, Auction.py:74).  The four winner-side sums of one opportunity {net, gross, overbid, wins} go out as ONE
-// 128-bit vector reduction (red.global.add.v4.f32, sm_90+) into a float scratch block [R][A][kK4Buckets][8] that is
-// bucketed by CTA (short float partial sums, less same-address contention); k4_fold_kernel adds the scratch into the
-// FP64 accumulators and clears it.  Shared-memory float atomics (a CAS loop on this architecture) and one FP64 atomic
-// per metric were both measured ~4x slower.
-constexpr int kK4Buckets = 8;
-__global__ void __launch_bounds__(256) k4_kernel_p2_acc(const SimParams p, const float4* __restrict__ bid, const float4* __restrict__ ctr,
-                                                        const float4* __restrict__ val, const uint2* __restrict__ parts,
-                                                        uint32_t* __restrict__ winner, float4* __restrict__ price,
-                                                        float4* __restrict__ second, uint32_t* __restrict__ outcome, long long N4,
-                                                        float* __restrict__ scratch) {
-  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= N4) return;
-  const long long n0 = q * 4;
-  const int run = int(n0 / p.T);
-  const long long t0 = n0 - (long long)run * p.T;
-  const PhiloxKey key = make_key(p.seed, uint32_t(p.run_offset + run));
-  const uint4 w = click_block(p.round0 + t0, p.iter, key);
-  const float4 b0 = __ldg(bid + 2 * q), b1 = __ldg(bid + 2 * q + 1);
-  const float4 c0 = __ldg(ctr + 2 * q), c1 = __ldg(ctr + 2 * q + 1);
-  const float4 v0 = __ldg(val + 2 * q), v1 = __ldg(val + 2 * q + 1);
-  const uint2 pa = __ldg(parts + q);
-  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-  const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-  const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-  const uint32_t uu[4] = {w.x, w.y, w.z, w.w};
-  float pr[4], se[4], rev = 0.0f;
-  uint32_t wpack = 0, opack = 0;
-  const bool first = p.mechanism == AGYM_FIRST_PRICE;
-  float* __restrict__ mine = scratch + ((size_t)run * p.A * kK4Buckets + (blockIdx.x % kK4Buckets)) * 8;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float x = bb[2 * j], y = bb[2 * j + 1];
-    const int ws = y > x ? 1 : 0;  // lowest slot on ties
-    const float hi = ws ? y : x, lo = ws ? x : y;
-    se[j] = lo;
-    pr[j] = first ? hi : lo;
-    const bool click = u32_to_unit(uu[j]) < cc[2 * j + ws];
-    wpack |= uint32_t(ws) << (8 * j);
-    opack |= uint32_t(click) << (8 * j);
-    const uint32_t pw = (j < 2 ? pa.x : pa.y) >> (16 * (j & 1));
-    const int ag_w = int((pw >> (8 * ws)) & 0xFF), ag_l = int((pw >> (8 * (1 - ws))) & 0xFF);
-    const float got = click ? vv[2 * j + ws] : 0.0f;
-    atomicAdd(reinterpret_cast<float4*>(mine + (size_t)ag_w * kK4Buckets * 8), make_float4(got - pr[j], got, pr[j] - lo, 1.0f));
-    const float tv_l = cc[2 * j + 1 - ws] * vv[2 * j + 1 - ws];
-    if (pr[j] < tv_l && pr[j] != lo) atomicAdd(mine + (size_t)ag_l * kK4Buckets * 8 + 4, pr[j] - lo);  // the loser's bid is `lo`
-    rev += pr[j];
-  }
-  winner[q] = wpack;
-  outcome[q] = opack;
-  price[q] = make_float4(pr[0], pr[1], pr[2], pr[3]);
-  second[q] = make_float4(se[0], se[1], se[2], se[3]);
-  // revenue: one atomic per warp when the warp sits inside one run (Auction.py:74)
-  const unsigned full = __activemask();
-  const int run_lo = __shfl_sync(full, run, __ffs(full) - 1);
-  if (full == 0xffffffffu && __all_sync(full, run == run_lo)) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) rev += __shfl_xor_sync(full, rev, off);
-    if ((threadIdx.x & 31) == 0) atomicAdd(p.revenue + run, double(rev));
+// 104-112, Auction.py:74).  A CTA walks kK4ChunksPerCta chunks of kK4Chunk consecutive opportunities of ONE run (thread =
+// 4 opportunities per chunk, 128-bit loads / stores).  The CTA keeps one histogram [A] x {net, gross, overbid,
+// underbid} of FIXED-POINT sums (2^-32, two 32-bit words) plus a win counter in shared memory and charges it with
+// native fire-and-forget shared-memory integer atomics (k4_add_fixed): integer addition commutes, so the result is
+// exact to 2^-32 per term and bit-reproducible whatever the order, and lanes that charge the same agent need no
+// software arbitration.
+// At the end the CTA stores per-agent doubles to its own slot of
+// scratch [R][CTAs per run][A * 5 + 1] (the last value is the CTA's revenue); the last CTA of a run to finish (one
+// counter per run) adds the run's slots in order into the FP64 accumulators.  Extra HBM traffic: under 1 %.
+// Measured and rejected on B200 (512 runs x 10 000 rounds, 184 MB algorithmic, L2 flushed): one red.global.add.v4.f32
+// per opportunity (round 1) 88 us = 0.32 of the HBM peak, bound by the L2 atomic units; float read-modify-write with
+// __match_any_sync ranks, one rank per round, 67 - 72 us (650 warp instructions per 128 opportunities, half of the issue
+// slots idle on the shared-memory round trips); redux.sync over each group's mask 240 us (a reduction per distinct mask
+// serialises); 64-bit fixed point as atom.shared.add.u64 (a CAS spin on this architecture) or as two 32-bit adds with a
+// carry taken from the returned old value 49 - 58 us (the returned value stalls the warp); shared-memory float atomics
+// are CAS loops as well.
+constexpr int kK4Chunk = 1024;      // opportunities per CTA and chunk
+constexpr int kK4Vals = 5;          // per-agent sums kept by the staged kernel: net, gross, overbid, underbid, wins
+constexpr int kK4MaxA = 256;        // uint8 agent ids
+// v = C * 2^-12 + F * 2^-32 with integers C = rint(v * 2^12) and F = rint((v - C * 2^-12) * 2^32), |F| <= 2^19: two
+// fire-and-forget 32-bit atomics per value (no returned value to wait for, no carry).  A CTA charges at most
+// kK4ChunksPerCta * kK4Chunk = 2048 opportunities to one agent, so |v| < 64 cannot overflow either word; larger values
+// (no shipped catalog has them: V ~ LogNormal(0.1, 0.2)) go to a float cell through the CAS loop.
+// Layout [value][C, F, overflow][A]: the same word of consecutive agents sits in consecutive banks.
+constexpr int kK4Words = 3;
+__device__ __forceinline__ void k4_add_fixed(int* __restrict__ hist, int A, int value, int agent, float v) {
+  int* cell = hist + (kK4Words * value) * A + agent;
+  if (fabsf(v) < 64.0f) {
+    const float c = rintf(v * 4096.0f);
+    const float r = fmaf(c, -1.0f / 4096.0f, v);  // exact
+    atomicAdd(cell, int(c));
+    atomicAdd(cell + A, __float2int_rn(r * 4294967296.0f));
   } else {
-    atomicAdd(p.revenue + run, double(rev));
+    atomicAdd(reinterpret_cast<float*>(cell + 2 * A), v);
   }
 }
+__device__ __forceinline__ double k4_read_fixed(const int* __restrict__ hist, int A, int value, int agent) {
+  const int* cell = hist + (kK4Words * value) * A + agent;
+  return double(cell[0]) * (1.0 / 4096.0) + double(cell[A]) * (1.0 / 4294967296.0) + double(__int_as_float(cell[2 * A]));
+}
 
-// scratch [R*A][kK4Buckets][8] -> acc [R*A][12] (FP64), scratch cleared; one thread per (run, agent)
-__global__ void __launch_bounds__(256) k4_fold_kernel(float* __restrict__ scratch, double* __restrict__ acc, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double s[5] = {0, 0, 0, 0, 0};
-  float4* sc = reinterpret_cast<float4*>(scratch + (size_t)i * kK4Buckets * 8);
+template <int kK4ChunksPerCta, int kMinBlocks>  // chunks a CTA walks with one histogram (zeroed and folded once)
+__global__ void __launch_bounds__(256, kMinBlocks) k4_kernel_p2_acc(const SimParams p, const float4* __restrict__ bid, const float4* __restrict__ ctr,
+                                                           const float4* __restrict__ val, const uint2* __restrict__ parts,
+                                                           uint32_t* __restrict__ winner, float4* __restrict__ price,
+                                                           float4* __restrict__ second, uint32_t* __restrict__ outcome, int ppr,
+                                                           double* __restrict__ scratch, int* __restrict__ done) {
+  extern __shared__ __align__(16) int k4_hist[];  // [4 values][C, F, overflow][A] fixed point, then int [A] wins, then float [8] revenue per warp
+  __shared__ int s_last;
+  static_assert(kK4ChunksPerCta * kK4Chunk <= 2048, "k4_add_fixed: overflow bound");
+  const int A = p.A, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int run = blockIdx.x / ppr, part = blockIdx.x - run * ppr;
+  int* __restrict__ wins = k4_hist + (size_t)A * 4 * kK4Words;
+  float* __restrict__ wrev = reinterpret_cast<float*>(wins + A);
+  for (int i = threadIdx.x; i < A * (4 * kK4Words + 1); i += 256) k4_hist[i] = 0;  // one histogram per CTA: the atomics arbitrate between warps too
+  __syncthreads();
+  const PhiloxKey key = make_key(p.seed, uint32_t(p.run_offset + run));
+  const bool first = p.mechanism == AGYM_FIRST_PRICE;
+  float rev = 0.0f;
+  for (int c = 0; c < kK4ChunksPerCta; ++c) {
+    const long long tc = ((long long)part * kK4ChunksPerCta + c) * kK4Chunk;
+    if (tc >= p.T) break;  // uniform across the CTA
+    const long long t0 = tc + 4 * threadIdx.x;
+    if (t0 >= p.T) continue;  // the run's last chunk is partial
+    const long long q = ((long long)run * p.T + t0) >> 2;
+    // streamed once: evict-first loads and stores
+    const float4 b0 = __ldcs(bid + 2 * q), b1 = __ldcs(bid + 2 * q + 1);
+    const float4 c0 = __ldcs(ctr + 2 * q), c1 = __ldcs(ctr + 2 * q + 1);
+    const float4 v0 = __ldcs(val + 2 * q), v1 = __ldcs(val + 2 * q + 1);
+    const uint2 pa = __ldcs(parts + q);
+    const uint4 w = click_block(p.round0 + t0, p.iter, key);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const uint32_t uu[4] = {w.x, w.y, w.z, w.w};
+    float pr[4], se[4];
+    uint32_t wpack = 0, opack = 0;
 #pragma unroll
-  for (int b = 0; b < kK4Buckets; ++b) {
-    const float4 u = sc[2 * b], v = sc[2 * b + 1];
-    s[0] += u.x; s[1] += u.y; s[2] += u.z; s[3] += u.w; s[4] += v.x;
-    sc[2 * b] = make_float4(0.f, 0.f, 0.f, 0.f);
-    sc[2 * b + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < 4; ++j) {
+      const float x = bb[2 * j], y = bb[2 * j + 1];
+      const int ws = y > x ? 1 : 0;  // lowest slot on ties
+      const float hi = ws ? y : x, lo = ws ? x : y;
+      se[j] = lo;
+      pr[j] = first ? hi : lo;
+      const float c_w = ws ? cc[2 * j + 1] : cc[2 * j], c_l = ws ? cc[2 * j] : cc[2 * j + 1];  // selects: no dynamically indexed arrays
+      const float v_w = ws ? vv[2 * j + 1] : vv[2 * j], v_l = ws ? vv[2 * j] : vv[2 * j + 1];
+      const bool click = u32_to_unit(uu[j]) < c_w;
+      wpack |= uint32_t(ws) << (8 * j);
+      opack |= uint32_t(click) << (8 * j);
+      const uint32_t pw = (j < 2 ? pa.x : pa.y) >> (16 * (j & 1));
+      const int ag0 = int(pw & 0xFF), ag1 = int((pw >> 8) & 0xFF);
+      const int ag_w = ws ? ag1 : ag0, ag_l = ws ? ag0 : ag1;
+      const float got = click ? v_w : 0.0f;
+      k4_add_fixed(k4_hist, A, 0, ag_w, got - pr[j]);                  // net utility      (Agent.py:72-73)
+      if (click) k4_add_fixed(k4_hist, A, 1, ag_w, got);               // gross utility    (Agent.py:74)
+      if (pr[j] != lo) k4_add_fixed(k4_hist, A, 2, ag_w, pr[j] - lo);  // overbid regret   (Agent.py:104-106): first price only
+      atomicAdd(wins + ag_w, 1);
+      if (pr[j] < c_l * v_l && pr[j] != lo) k4_add_fixed(k4_hist, A, 3, ag_l, pr[j] - lo);  // underbid regret; the loser's bid is `lo`
+      rev += pr[j];
+    }
+    __stcs(winner + q, wpack);
+    __stcs(outcome + q, opack);
+    __stcs(price + q, make_float4(pr[0], pr[1], pr[2], pr[3]));
+    __stcs(second + q, make_float4(se[0], se[1], se[2], se[3]));
   }
-  double* a = acc + (size_t)i * kNumMetrics;
-  a[AGYM_M_NET] += s[0]; a[AGYM_M_GROSS] += s[1]; a[AGYM_M_OVERBID_REGRET] += s[2]; a[AGYM_M_NWON] += s[3];
-  a[AGYM_M_UNDERBID_REGRET] += s[4];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) rev += __shfl_xor_sync(0xffffffffu, rev, off);
+  if (lane == 0) wrev[warp] = rev;
+  __syncthreads();
+  const int stride = A * kK4Vals + 1;
+  double* __restrict__ out = scratch + ((size_t)run * ppr + part) * stride;
+  for (int i = threadIdx.x; i < A * 4; i += 256) {
+    const int v = i / A, a = i - v * A;
+    out[a * kK4Vals + v] = k4_read_fixed(k4_hist, A, v, a);
+  }
+  for (int a = threadIdx.x; a < A; a += 256) out[a * kK4Vals + 4] = double(wins[a]);
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    for (int wi = 0; wi < 8; ++wi) sum += wrev[wi];
+    out[A * kK4Vals] = double(sum);
+  }
+  // the run's last CTA to finish adds the run's partial sums, in part order, into the FP64 accumulators
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(done + run, 1) == ppr - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double* __restrict__ src = scratch + (size_t)run * ppr * stride;
+  for (int i = threadIdx.x; i <= A * kK4Vals; i += 256) {
+    double sum = 0.0;
+    for (int c = 0; c < ppr; ++c) sum += __ldcg(src + (size_t)c * stride + i);
+    if (i == A * kK4Vals) { p.revenue[run] += sum; continue; }
+    const int a = i / kK4Vals, k = i - a * kK4Vals;
+    const int col = k == 0 ? AGYM_M_NET : k == 1 ? AGYM_M_GROSS : k == 2 ? AGYM_M_OVERBID_REGRET : k == 3 ? AGYM_M_UNDERBID_REGRET : AGYM_M_NWON;
+    p.acc[((size_t)run * A + a) * kNumMetrics + col] += sum;
+  }
+  if (threadIdx.x == 0) done[run] = 0;  // ready for the next launch
 }
 
 // general P: one thread per opportunity, running top-2
@@ -367,18 +425,26 @@ int launch_k4(agym_handle* h, const SimParams& p, const float* bid, const float*
                        ((uintptr_t)second % 16 == 0) && ((uintptr_t)outcome % 4 == 0);
   if (p.P == 2 && p.T % 4 == 0 && p.round0 % 4 == 0 && aligned) {
     const long long N4 = N / 4;
-    if (accumulate) {
-      const size_t nsc = (size_t)p.R * p.A * kK4Buckets * 8;
-      if (h->k4_scratch == nullptr) {  // first use: allocate + clear (configuration-time cost, synchronous)
-        cudaError_t e = cudaMalloc(&h->k4_scratch, nsc * sizeof(float));
-        if (e == cudaSuccess) e = cudaMemset(h->k4_scratch, 0, nsc * sizeof(float));
+    if (accumulate && p.A <= kK4MaxA) {
+      const int chunks = int((p.T + kK4Chunk - 1) / kK4Chunk);
+      constexpr int cpc = 2;  // B200, 512 runs: 1 -> 55 us, 2 -> 49 us, 5 -> 51 us (with the 64-bit variant); 5 / 6 / 4 CTAs per SM -> 49 / 51 / 51 us
+      const int ppr = (chunks + cpc - 1) / cpc;  // CTAs (= partial-sum slots) per run
+      const size_t nfl = (size_t)p.R * ppr * (p.A * kK4Vals + 1);
+      const size_t nsc = nfl * sizeof(double) + (size_t)p.R * sizeof(int);
+      if (h->k4_scratch == nullptr || h->k4_scratch_bytes != nsc) {  // first use: allocate + clear the counters (configuration-time, synchronous)
+        cudaFree(h->k4_scratch);
+        h->k4_scratch = nullptr;
+        cudaError_t e = cudaMalloc(&h->k4_scratch, nsc);
+        if (e == cudaSuccess) e = cudaMemset(h->k4_scratch, 0, nsc);
         if (e != cudaSuccess) return check_cuda(h, e, "k4 scratch");
+        h->k4_scratch_bytes = nsc;
       }
-      k4_kernel_p2_acc<<<unsigned((N4 + 255) / 256), 256, 0, s>>>(p, (const float4*)bid, (const float4*)true_ctr, (const float4*)value,
-                                                                 (const uint2*)parts, (uint32_t*)winner, (float4*)price,
-                                                                 (float4*)second, (uint32_t*)outcome, N4, h->k4_scratch);
-      k4_fold_kernel<<<unsigned((p.R * p.A + 255) / 256), 256, 0, s>>>(h->k4_scratch, p.acc, p.R * p.A);
-      h->launches += 2;
+      const size_t smem = (size_t)p.A * (4 * kK4Words + 1) * sizeof(int) + 8 * sizeof(float);
+      k4_kernel_p2_acc<cpc, 5><<<unsigned(p.R) * unsigned(ppr), 256, smem, s>>>(
+          p, (const float4*)bid, (const float4*)true_ctr, (const float4*)value, (const uint2*)parts, (uint32_t*)winner, (float4*)price,
+          (float4*)second, (uint32_t*)outcome, ppr, reinterpret_cast<double*>(h->k4_scratch),
+          reinterpret_cast<int*>(reinterpret_cast<double*>(h->k4_scratch) + nfl));
+      h->launches += 1;
       return check_cuda(h, cudaGetLastError(), "k4_kernel_p2_acc");
     }
     k4_kernel_p2<<<unsigned((N4 + 255) / 256), 256, 0, s>>>(p, (const float4*)bid, (const float4*)true_ctr, (const float4*)value,

@@ -470,11 +470,10 @@ def main():
                                        "from_profile": profile_numbers(r"fit_warp_kernel<3", R * A)}
     aux = {}
     if not args.no_aux:
-        # staged resolution kernel K4(+K5) on the same opportunities: HBM-bound, 13P+10 = 36 B/opportunity
-        Rk = min(R, 512)
-        engk = eng if Rk == R else make_engine(ag, _lib, Rk, T, learnt, local_rank, first_run)
-        if engk is not eng and learnt:
-            engk.set_allocator_state(m0_host[:Rk])
+        # staged resolution kernel K4(+K5) on this GPU's resident runs: HBM-bound.  With the per-agent accumulation it moves
+        # 13P + 10 = 36 B/opportunity; resolution + click alone never reads the values and agent ids: 8P + 10 = 26 B
+        Rk = R
+        engk = eng
         engk.clear_iteration()
         b = engk.staged_round(SEED, 0, T)
         flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # 4x the 126 MB L2
@@ -490,16 +489,15 @@ def main():
                 torch.cuda.synchronize(dev)
                 ts.append(s.elapsed_time(e))
             ms4 = float(np.mean(ts))
-            by = Rk * T * (13 * P + 10)
+            by = Rk * T * ((13 * P + 10) if accumulate else (8 * P + 10))
             prof = profile_numbers(r"k4_kernel_p2_acc" if accumulate else r"k4_kernel_p2\b", None)
             aux["k4_resolve" + ("+accumulate" if accumulate else "")] = {
                 "bound": "hbm", "achieved": by / ms4 / 1e6, "peak": peak, "unit": "GB/s", "frac": by / ms4 / 1e6 / peak,
                 "ms": ms4, "algorithmic_bytes": by, "opportunities_per_s": Rk * T / ms4 * 1e3,
                 "traffic": prof["dram_bytes"] if prof else None, "from_profile": prof,
+                "bytes_per_opportunity": (13 * P + 10) if accumulate else (8 * P + 10),
                 "note": f"{Rk * T} opportunities, {by / 1e6:.0f} MB algorithmic; L2 flushed (512 MB fill) before every timed launch; outside the timed step"}
         del b, flush
-        if engk is not eng:
-            engk.close()
     dominant = max(kernels.items(), key=lambda kv: kv[1]["ms"])
     dprof = dominant[1].get("from_profile")
     roofline = {"kernel": dominant[0], "bound": "hbm", "achieved": dominant[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",
