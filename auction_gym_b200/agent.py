@@ -53,11 +53,27 @@ class Agent:
             return []
         return self._auction._agent_logs(self._index)
 
-    def select_item(self, context):
-        raise NotImplementedError("select_item runs inside the engine for whole batches (agym_simulate_rounds)")
+    def select_item(self, context, _eps=None):
+        """Agent.py:29-42 for one context: arg-max of estimated CTR x item value (first maximum); a Thompson-sampling
+        allocator chooses on the sampled estimates and reports the MAP estimate of the chosen item."""
+        from .allocators import OracleAllocator
 
-    def bid(self, context):
-        raise NotImplementedError("bid runs inside the engine for whole batches (agym_simulate_rounds)")
+        if isinstance(self.allocator, OracleAllocator):
+            estim_CTRs = self.allocator.estimate_CTR(context)
+        else:
+            estim_CTRs = self.allocator.estimate_CTR(context, _eps=_eps)
+        best_item = int(np.argmax(estim_CTRs * np.asarray(self.item_values)))
+        if not isinstance(self.allocator, OracleAllocator) and self.allocator.thompson_sampling:
+            estim_CTRs = self.allocator.estimate_CTR(context, sample=False)
+        return best_item, estim_CTRs[best_item]
+
+    def bid(self, context, _eps=None):
+        """Agent.py:44-68 for one context: (bid, chosen item).  A query: the engine keeps its own per-round log when it
+        simulates (agym_simulate_rounds), so nothing is appended to ``logs`` here."""
+        best_item, estimated_CTR = self.select_item(context, _eps=_eps)
+        value = self.item_values[best_item]
+        bid = self.bidder.bid(value, context, estimated_CTR)
+        return bid, best_item
 
     def update(self, iteration, plot=False, figsize=(8, 5), fontsize=14):
         """Agent.py:79-94: allocator.update on the won rows, bidder.update on all rows.  The engine fits

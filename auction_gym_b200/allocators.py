@@ -22,6 +22,16 @@ class Allocator:
     def _attach(self, auction, index):
         self._auction, self._index = auction, index
 
+    def _estimate(self, context, sample, _eps=None):
+        """One context through agym_estimate_ctr (the engine is built on first use, as simulate_opportunity would)."""
+        au = self._auction
+        if au is None:
+            raise RuntimeError("estimate_CTR needs the agent to be part of an Auction (the catalog and the learnt state live in its engine)")
+        if au.engine is None:
+            au._build()
+        au._queries += 1
+        return au.engine.estimate_ctr(self._index, context, sample=sample, eps=_eps, seed=au.seed, iteration=au.iteration, query=au._queries)
+
     def update(self, contexts, items, outcomes, iteration, plot, figsize, fontsize, name):
         """The reference passes the agent's logged rows; here the rows already live on the device, so the
         arguments are ignored and the batched fit of the attached auction runs (once per iteration)."""
@@ -73,9 +83,11 @@ class PyTorchLogisticRegressionAllocator(Allocator):
         self._init_q = np.ones((self.num_items, self.embedding_size + 1), np.float32)
         self.response_model = ResponseModelView(self)
 
-    def estimate_CTR(self, context, sample=True):
-        raise NotImplementedError("estimate_CTR runs inside the engine for whole batches of opportunities "
-                                  "(agym_simulate_rounds); there is no per-context host path")
+    def estimate_CTR(self, context, sample=True, _eps=None):
+        """BidderAllocation.py:67-68: float32 estimates of every item for one observed context [Do + 1]; a Thompson draw when
+        ``thompson_sampling and sample``.  ``_eps`` ([num_items, Do + 1] standard normals) replays a given draw (tests)."""
+        est = self._estimate(context, bool(self.thompson_sampling and sample), _eps)
+        return est[:self.num_items].astype(np.float32)
 
 
 # the stale name used in the reference's own comment (src/main.py:16) and in BASELINE.json
@@ -95,4 +107,5 @@ class OracleAllocator(Allocator):
         self.item_embeddings = item_embeddings
 
     def estimate_CTR(self, context):
-        raise NotImplementedError("estimate_CTR runs inside the engine for whole batches of opportunities")
+        """BidderAllocation.py:81-82: sigmoid(item_embeddings @ context) for one true context [D + 1], float64."""
+        return self._estimate(context, False)[:len(self.item_embeddings)]

@@ -50,6 +50,7 @@ class Auction:
         self.engine = None
         self._rounds_capacity = int(rounds_capacity)
         self._models_updated = False
+        self._queries = 0       # per-context host queries so far (estimate_CTR / select_item / bid): their Philox counter
         self._cleared = set()
         self._log_chunks = []   # detailed log of run 0 for the current iteration (list of dicts of numpy arrays)
         self._log_cache = None
@@ -200,6 +201,33 @@ class Auction:
             self._log_chunks, self._log_cache = [], None
             self._cleared = set()
             self.iteration += 1
+
+    # ------------------------------------------------------------------ checkpoint
+    def save_checkpoint(self, path, **extra):
+        """Learnt state of every resident run at an iteration boundary -> ``path`` (.npz); ``extra`` arrays ride along
+        (the driver stores the metrics collected so far).  The reference has no counterpart."""
+        if self.engine is None:
+            self._build()
+        d = self.engine.save_state()
+        d.update(iteration=np.int64(self.iteration), seed=np.int64(self.seed), run_offset=np.int64(self.run_offset), **extra)
+        tmp = str(path) + ".tmp.npz"
+        np.savez(tmp, **d)
+        import os
+
+        os.replace(tmp, str(path))
+
+    def load_checkpoint(self, path):
+        """Resume from ``save_checkpoint``: same config, same seed, same shard.  Returns the stored dict."""
+        if self.engine is None:
+            self._build()
+        d = dict(np.load(str(path)))
+        if int(d["seed"]) != self.seed or int(d["run_offset"]) != self.run_offset:
+            raise _lib.AgymError(f"checkpoint of seed {int(d['seed'])} / first run {int(d['run_offset'])} does not belong to this auction "
+                                 f"(seed {self.seed}, first run {self.run_offset})")
+        self.engine.load_state(d)
+        self.iteration = int(d["iteration"])
+        self._models_updated = False
+        return d
 
     def end_iteration(self):
         """Batched equivalent of main.py:151-155 for all agents: clear utilities, logs and revenue."""

@@ -30,6 +30,20 @@ class Bidder:
         if self._auction is not None:
             self._auction._update_models()
 
+    def bid(self, value, context, estimated_CTR):
+        """Bidder.bid (Bidder.py:34-35,47-58,171-208,348-367,455-475) for one opportunity: a T = 1 launch of the staged bid
+        kernel (agym_k3_bids) with this agent's current state (shading noise from Philox, keyed by the auction seed, the
+        iteration and a query counter)."""
+        au = self._auction
+        if au is None:
+            raise RuntimeError("bid needs the agent to be part of an Auction (the bidder state lives in its engine)")
+        if au.engine is None:
+            au._build()
+        au._queries += 1
+        b, g, p = au.engine.bid_one(self._index, estimated_CTR, value, seed=au.seed + 0x9E3779B97F4A7C15 * au._queries, iteration=au.iteration)
+        self._last_gamma, self._last_propensity = g, p
+        return b
+
     def clear_logs(self, memory):
         pass
 

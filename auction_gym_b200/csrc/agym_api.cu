@@ -132,7 +132,7 @@ int agym_destroy(agym_handle* h) {
   cudaFree(h->d_n_items); cudaFree(h->d_alloc_kind); cudaFree(h->d_bidder_kind); cudaFree(h->d_bidder_fit);
   cudaFree(h->d_E64); cudaFree(h->d_V64); cudaFree(h->d_E32); cudaFree(h->d_V32);
   cudaFree(h->d_memory); cudaFree(h->d_mem_off);
-  cudaFree(h->d_fit_epochs);
+  cudaFree(h->d_fit_epochs); cudaFree(h->est_scratch);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -157,6 +157,7 @@ int agym_set_agents(agym_handle* h, const int32_t* n_items, const int32_t* alloc
     h->any_unbuilt_fit |= bidder_kind[a] == AGYM_BID_BANDIT || bidder_kind[a] == AGYM_BID_POLICY;
     if (n_items[a] > h->max_items) h->max_items = n_items[a];
   }
+  h->alloc_kind_host.assign(alloc_kind, alloc_kind + A);
   cudaError_t e = cudaMemcpy(h->d_n_items, n_items, A * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_alloc_kind, alloc_kind, A * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_bidder_kind, bidder_kind, A * sizeof(int), cudaMemcpyHostToDevice);
@@ -413,6 +414,39 @@ static int staged_params(agym_handle* h, uint64_t seed, int32_t iter, int64_t T,
   *p = make_params(h);
   p->T = T; p->seed = seed; p->iter = iter; p->round0 = 0;
   return AGYM_OK;
+}
+
+int agym_estimate_ctr(agym_handle* h, int32_t run, int32_t agent, const double* context, int32_t sample, const float* eps, uint64_t seed,
+                      int32_t iter, int64_t query, double* out, void* stream) {
+  if (!h || !context || !out) return set_error(h, AGYM_ERR_INVALID, "agym_estimate_ctr: null argument");
+  const agym_shape& sh = h->shape;
+  if (run < 0 || run >= sh.R || agent < 0 || agent >= sh.A) return set_error(h, AGYM_ERR_INVALID, "agym_estimate_ctr: run / agent out of range");
+  if (!h->agents_set || !h->catalog_set) return set_error(h, AGYM_ERR_STATE, "agym_estimate_ctr: configuration incomplete");
+  if (h->any_learnt && (!h->m || !h->sigma)) return set_error(h, AGYM_ERR_STATE, "agym_estimate_ctr: allocator state not bound");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nctx = size_t(sh.D + 1), neps = size_t(sh.I) * h->K, nout = size_t(sh.I);
+  const size_t bytes = (nctx + nout) * sizeof(double) + neps * sizeof(float);
+  if (!h->est_scratch) {
+    cudaError_t e = cudaMalloc(&h->est_scratch, bytes);
+    if (e != cudaSuccess) return check_cuda(h, e, "agym_estimate_ctr: scratch");
+  }
+  double* d_ctx = static_cast<double*>(h->est_scratch);
+  double* d_out = d_ctx + nctx;
+  float* d_eps = reinterpret_cast<float*>(d_out + nout);
+  std::vector<double> cpad(nctx, 0.0);
+  const bool oracle = h->alloc_kind_host[agent] == AGYM_ALLOC_ORACLE;
+  for (size_t i = 0; i < (oracle ? nctx : size_t(h->K)); ++i) cpad[i] = context[i];  // Oracle agents see the true context, learnt ones the observed one (Auction.py:46-49)
+  cudaError_t e = cudaMemcpyAsync(d_ctx, cpad.data(), nctx * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && eps) e = cudaMemcpyAsync(d_eps, eps, neps * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return check_cuda(h, e, "agym_estimate_ctr: upload");
+  SimParams p = make_params(h);
+  p.seed = seed; p.iter = iter; p.round0 = query;
+  int rc = launch_estimate(h, p, run, agent, d_ctx, sample, eps ? d_eps : nullptr, d_out, st);
+  if (rc) return rc;
+  e = cudaMemcpyAsync(out, d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the reference's estimate_CTR returns a host array
+  return check_cuda(h, e, "agym_estimate_ctr: download");
 }
 
 int agym_k1_contexts(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, float* ctx, uint8_t* parts, void* stream) {

@@ -6,6 +6,7 @@
 
 #include <map>
 #include <string>
+#include <vector>
 
 #include "agym.h"
 
@@ -190,6 +191,7 @@ struct agym_handle {
   int* d_bidder_kind = nullptr;
   int* d_bidder_fit = nullptr;
   int bidder_fit_host[4096];
+  std::vector<int32_t> alloc_kind_host;
   bool any_winrate_fit = false, any_policy_fit = false, any_unassigned_bandit = false, any_empirical_fit = false;
   double* d_E64 = nullptr;
   double* d_V64 = nullptr;
@@ -200,6 +202,7 @@ struct agym_handle {
   double* d_adam_sz0 = nullptr;  // [kAdamTable] 2e-3 / (1 - 0.9^t), t = epoch + 1 (torch Adam step size at lr 2e-3)
   float* d_adam_bc2s = nullptr;  // [kAdamTable] sqrt(1 - 0.999^t)
   float2* d_adam_ep = nullptr;   // [kAdamTable] {float(d_adam_sz0), d_adam_bc2s}: one 64-bit load per epoch
+  void* est_scratch = nullptr;   // device staging of agym_estimate_ctr: context, eps, output (lazy)
   float* k4_scratch = nullptr;   // [R][chunks][A * 5 + 1] float partial sums of the staged resolution kernel (lazy)
   size_t k4_scratch_bytes = 0;
   bool agents_set = false, catalog_set = false;
@@ -260,6 +263,8 @@ int launch_k2(agym_handle* h, const SimParams& p, const float* ctx, const uint8_
               float* true_ctr, float* best_ev, float* value, cudaStream_t s);
 int launch_k3(agym_handle* h, const SimParams& p, const uint8_t* parts, const float* est, const float* value, float* bid,
               float* gamma, float* propensity, cudaStream_t s);
+int launch_estimate(agym_handle* h, const SimParams& p, int run, int a, const double* ctx, int sample, const float* eps, double* out,
+                    cudaStream_t s);
 int launch_k4(agym_handle* h, const SimParams& p, const float* bid, const float* true_ctr, const float* value,
               const uint8_t* parts, uint8_t* winner, float* price, float* second, uint8_t* outcome, int accumulate,
               cudaStream_t s);

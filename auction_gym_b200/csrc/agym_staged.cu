@@ -415,6 +415,46 @@ __global__ void __launch_bounds__(256) k4_kernel_any(const SimParams p, const fl
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Allocator.estimate_CTR for ONE context: every item of one (run, agent), in the reference's precision mix
+// (OracleAllocator: float64, BidderAllocation.py:81-82; PyTorchLogisticRegressionAllocator: the context cast to float32,
+// weights m or m + eps / sqrt(q) with eps ~ N(0, 1) per weight, BidderAllocation.py:67-68, Models.py:28-33).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) estimate_kernel(const SimParams p, int run, int a, const double* __restrict__ ctx, int sample,
+                                                      const float* __restrict__ eps, double* __restrict__ out) {
+  using A_ = Arith<double>;
+  const int nI = p.n_items[a], K = p.Do + 1;
+  const PhiloxKey key = make_key(p.seed, uint32_t(p.run_offset + run));
+  for (int i = threadIdx.x; i < nI; i += blockDim.x) {
+    if (p.alloc_kind[a] == AGYM_ALLOC_ORACLE) {
+      const double* __restrict__ e = p.E64 + ((size_t)a * p.I + i) * (p.D + 1);
+      double z = 0.0;
+      for (int d = 0; d <= p.D; ++d) z = fma(ctx[d], e[d], z);
+      out[i] = A_::sigmoid(z);
+      continue;
+    }
+    const size_t o = (((size_t)run * p.A + a) * p.I + i) * K;
+    float zl = 0.0f;
+    for (int kb = 0; kb * 4 < K; ++kb) {
+      float4 nrm = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sample && !eps) nrm = philox_normal4(uint32_t(p.round0), uint32_t(p.iter) ^ (uint32_t(p.round0 >> 32) << 20), kPurposeTS << 16, uint32_t(i * 16 + kb), key);
+      for (int j = 0; j < 4 && kb * 4 + j < K; ++j) {
+        const int k = kb * 4 + j;
+        float w = p.m[o + k];
+        if (sample) w = A_::ts_weight(w, eps ? eps[(size_t)i * K + k] : pick4<float>(nrm, j), p.sigma[o + k]);  // Models.py:31
+        zl = A_::mac(w, float(ctx[k]), zl);
+      }
+    }
+    out[i] = double(A_::sigmoid32(zl));
+  }
+}
+
+int launch_estimate(agym_handle* h, const SimParams& p, int run, int a, const double* ctx, int sample, const float* eps, double* out, cudaStream_t s) {
+  estimate_kernel<<<1, 64, 0, s>>>(p, run, a, ctx, sample, eps, out);
+  h->launches += 1;
+  return check_cuda(h, cudaGetLastError(), "estimate_kernel");
+}
+
 int launch_k4(agym_handle* h, const SimParams& p, const float* bid, const float* true_ctr, const float* value,
               const uint8_t* parts, uint8_t* winner, float* price, float* second, uint8_t* outcome, int accumulate,
               cudaStream_t s) {

@@ -136,10 +136,18 @@ def iteration_block(auction):
     return blk, rev
 
 
-def simulation_run(auction, num_iter, rounds_per_iter, verbose=False):
-    """main.py:112-155 for every resident run at once.  Returns metrics [R, N, A, 10] and revenue [R, N]."""
+def simulation_run(auction, num_iter, rounds_per_iter, verbose=False, checkpoint=None, resume=False):
+    """main.py:112-155 for every resident run at once.  Returns metrics [R, N, A, 10] and revenue [R, N].
+    ``checkpoint`` (a path): the learnt state and the metrics so far are written after every iteration; ``resume`` continues
+    from that file, and the result equals an uninterrupted job bit for bit (same seed, same Philox counters)."""
     blocks, revs = [], []
-    for i in range(num_iter):
+    first = 0
+    if checkpoint and resume and os.path.isfile(checkpoint):
+        d = auction.load_checkpoint(checkpoint)
+        first = auction.iteration
+        blocks = [d["metrics"][:, i] for i in range(first)]
+        revs = [d["revenue_so_far"][:, i] for i in range(first)]
+    for i in range(first, num_iter):
         auction.simulate_rounds(rounds_per_iter)
         auction._update_models()  # agent.update() of every agent (main.py:128-129)
         blk, rev = iteration_block(auction)
@@ -148,6 +156,8 @@ def simulation_run(auction, num_iter, rounds_per_iter, verbose=False):
         blocks.append(blk)
         revs.append(rev)
         auction.end_iteration()  # clear_utility / clear_logs / clear_revenue (main.py:151-155)
+        if checkpoint:
+            auction.save_checkpoint(checkpoint, metrics=np.stack(blocks, axis=1), revenue_so_far=np.stack(revs, axis=1))
     return np.stack(blocks, axis=1), np.stack(revs, axis=1)
 
 
@@ -172,7 +182,7 @@ def gather_runs(local, world):
     return np.concatenate([p[:int(c.item())].cpu().numpy() for p, c in zip(parts, counts)], axis=0)
 
 
-def run_experiment(config_path, device=0, rank=0, world=1, precision=None, verbose=False):
+def run_experiment(config_path, device=0, rank=0, world=1, precision=None, verbose=False, checkpoint_dir=None, resume=False, stop_after=None):
     """Parse the config, simulate this rank's share of the runs, gather.  Returns a dict with the reference's
     run -> agent -> per-iteration structure flattened into arrays (see ``write_csvs``)."""
     rng, config, agent_configs, agents2items, agents2item_values, num_runs, max_slots, embedding_size, embedding_var, \
@@ -186,7 +196,12 @@ def run_experiment(config_path, device=0, rank=0, world=1, precision=None, verbo
             rng, config, agents2items, agents2item_values, agents, max_slots, embedding_size, embedding_var, obs_embedding_size,
             num_runs=count, run_offset=first, device=device, precision=precision, seed=config["random_seed"],
             rounds_capacity=config["rounds_per_iter"], per_run_init=True)
-        metrics, revenue = simulation_run(auction, num_iter, rounds_per_iter, verbose=verbose and rank == 0)
+        ckpt = None
+        if checkpoint_dir:
+            os.makedirs(checkpoint_dir, exist_ok=True)
+            ckpt = os.path.join(checkpoint_dir, f"state_rank{rank}_of_{world}.npz")
+        metrics, revenue = simulation_run(auction, num_iter if stop_after is None else min(num_iter, stop_after), rounds_per_iter,
+                                          verbose=verbose and rank == 0, checkpoint=ckpt, resume=resume)
         auction.engine.close()
     metrics = gather_runs(metrics, world)
     revenue = gather_runs(revenue, world)
@@ -249,6 +264,8 @@ def main(argv=None):
     parser.add_argument("config", type=str, help="Path to experiment configuration file")
     parser.add_argument("--output-dir", default=None)
     parser.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    parser.add_argument("--checkpoint-dir", default=None, help="write the learnt state after every iteration (one file per rank)")
+    parser.add_argument("--resume", action="store_true", help="continue from --checkpoint-dir")
     args = parser.parse_args(argv)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
@@ -258,7 +275,8 @@ def main(argv=None):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     result = run_experiment(args.config, device=local, rank=rank, world=world,
-                            precision=_lib.FP64 if args.precision == "fp64" else _lib.FP32, verbose=True)
+                            precision=_lib.FP64 if args.precision == "fp64" else _lib.FP32, verbose=True,
+                            checkpoint_dir=args.checkpoint_dir, resume=args.resume)
     if rank == 0:
         out = write_csvs(result, args.output_dir)
         print(f"wrote CSVs to {out}")

@@ -196,6 +196,46 @@ class Engine:
                 bw[..., 4:16] = np.broadcast_to(np.asarray(policy_w, np.float32), (self.R, self.A, 12))
             self.bidder_w.copy_(torch.from_numpy(bw))
 
+    # ------------------------------------------------------------------ checkpoint
+    def save_state(self):
+        """Everything that survives an iteration boundary, as host numpy arrays: the learnt allocator state (Models.py:21-24
+        m, q, prev_iter_m), the bidder state (prev_gamma, gamma_sigma, model_initialised, win-rate and policy weights) and,
+        with ``Agent(memory=...)``, the retained log rows plus the accumulators that restart from them.  Call it between
+        iterations (after clear_iteration): the rounds of an unfinished iteration are not part of the state."""
+        if self.rounds_in_iteration:
+            raise AgymError("save_state: call it at an iteration boundary (after clear_iteration / end_iteration)")
+        d = {"shape": np.array([self.R, self.A, self.I, self.D, self.Do, self.P, self.log_base], np.int64),
+             "bidder_d": self.bidder_d.cpu().numpy(), "bidder_w": self.bidder_w.cpu().numpy()}
+        if self.any_learnt:
+            d.update(m=self.m.cpu().numpy(), q=self.q.cpu().numpy(), m_prev=self.m_prev.cpu().numpy())
+        if self.retention:
+            d.update(acc=self.acc.cpu().numpy(), revenue=self.revenue.cpu().numpy())
+            for k in ("fit_ctx", "fit_meta", "bid_rows", "bid_meta", "terms"):
+                t = getattr(self, k)
+                if t is not None:
+                    d["log_" + k] = t[:, :self.log_base].cpu().numpy()
+        return d
+
+    def load_state(self, d):
+        """Inverse of save_state on an engine of the same shape and configuration."""
+        want = np.array([self.R, self.A, self.I, self.D, self.Do, self.P, self.log_base], np.int64)
+        if not np.array_equal(np.asarray(d["shape"]), want):
+            raise AgymError(f"load_state: checkpoint shape {list(np.asarray(d['shape']))} != engine shape {list(want)}")
+        self.bidder_d.copy_(torch.from_numpy(np.asarray(d["bidder_d"])))
+        self.bidder_w.copy_(torch.from_numpy(np.asarray(d["bidder_w"])))
+        if self.any_learnt:
+            self.set_allocator_state(np.asarray(d["m"]), np.asarray(d["q"]), np.asarray(d["m_prev"]))
+        if self.retention:
+            if self.rounds_capacity == 0:
+                self.reserve_rounds(1)
+            self._check(self.lib.agym_clear_iteration(self.handle, self._stream()))
+            self.acc.copy_(torch.from_numpy(np.asarray(d["acc"])))
+            self.revenue.copy_(torch.from_numpy(np.asarray(d["revenue"])))
+            for k in ("fit_ctx", "fit_meta", "bid_rows", "bid_meta", "terms"):
+                t = getattr(self, k)
+                if t is not None and "log_" + k in d:
+                    t[:, :self.log_base].copy_(torch.from_numpy(np.asarray(d["log_" + k])))
+
     # ------------------------------------------------------------------ round loop
     def _alloc_log(self, n_runs, T, fields):
         log = RoundLog()
@@ -326,6 +366,36 @@ class Engine:
         self._check(self.lib.agym_k4_resolve(self.handle, s, int(iteration), int(T), _ptr(b["bid"]), _ptr(b["true_ctr"]),
                                              _ptr(b["value"]), _ptr(b["parts"]), _ptr(b["winner"]), _ptr(b["price"]),
                                              _ptr(b["second"]), _ptr(b["outcome"]), 1 if accumulate else 0, self._stream()))
+
+    # ------------------------------------------------------------------ one context at a time (the reference's per-call surface)
+    def estimate_ctr(self, agent, context, sample=False, eps=None, seed=0, iteration=0, query=0, run=0):
+        """Allocator.estimate_CTR for one context (include/agym.h: agym_estimate_ctr): numpy float64 [I]."""
+        ctx = np.ascontiguousarray(context, dtype=np.float64)
+        need = (self.D if self.alloc_kind[agent] == _lib.ALLOC_ORACLE else self.Do) + 1
+        if ctx.shape != (need,):
+            raise ValueError(f"context has shape {ctx.shape}, expected ({need},) (the trailing 1 included, Auction.py:33-49)")
+        e = None if eps is None else np.ascontiguousarray(eps, dtype=np.float32)
+        if e is not None and e.shape != (self.I, self.Do + 1):
+            raise ValueError(f"eps has shape {e.shape}, expected {(self.I, self.Do + 1)}")
+        out = np.empty(self.I, np.float64)
+        self._check(self.lib.agym_estimate_ctr(self.handle, int(run), int(agent), ctx.ctypes.data, 1 if sample else 0,
+                                               None if e is None else e.ctypes.data, C.c_uint64(int(seed) & (2**64 - 1)), int(iteration),
+                                               int(query), out.ctypes.data, self._stream()))
+        return out
+
+    def bid_one(self, agent, estimated_ctr, value, seed=0, iteration=0, run=0):
+        """Bidder.bid for one (value, estimated CTR) of one agent through the staged K3 kernel (a T = 1 launch):
+        returns (bid, gamma, propensity); gamma / propensity are NaN for a TruthfulBidder."""
+        R, P, dev = self.R, self.P, self.device
+        others = [a for a in range(self.A) if a != agent][:P - 1]
+        parts = torch.tensor([[agent] + others] * R, dtype=torch.uint8, device=dev)
+        est = torch.zeros((R, P), dtype=torch.float32, device=dev)
+        val = torch.zeros((R, P), dtype=torch.float32, device=dev)
+        est[:, 0], val[:, 0] = float(estimated_ctr), float(value)
+        bid, gamma, prop = (torch.empty((R, P), dtype=torch.float32, device=dev) for _ in range(3))
+        self._check(self.lib.agym_k3_bids(self.handle, C.c_uint64(int(seed) & (2**64 - 1)), int(iteration), 1, _ptr(parts), _ptr(est), _ptr(val),
+                                          _ptr(bid), _ptr(gamma), _ptr(prop), self._stream()))
+        return float(bid[run, 0]), float(gamma[run, 0]), float(prop[run, 0])
 
     # ------------------------------------------------------------------ results
     def metrics(self):

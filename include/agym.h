@@ -191,6 +191,15 @@ int64_t agym_retained_capacity(const agym_handle* h);
  * Net / gross utility and revenue are NOT touched (Agent.clear_utility and Auction.clear_revenue are separate calls). */
 int agym_retain_logs(agym_handle* h, void* stream);
 
+/* Allocator.estimate_CTR for ONE context (BidderAllocation.py:67-68, 81-82; Models.py:28-33): the estimated CTR of every
+ * item of `agent` in resident run `run`.  context (HOST, D+1 doubles for an OracleAllocator agent -- the true context --,
+ * Do+1 for a learnt one; the trailing 1 included, Auction.py:33-49).  sample != 0: Thompson draw m + eps / sqrt(q) per weight,
+ * eps (HOST, nullable, [I][Do+1] float) supplied by the caller (replay) or drawn from Philox keyed by (seed, run, iter, query).
+ * out (HOST, I doubles; float32 values for learnt agents, as the reference returns).  Synchronises the stream: like the
+ * reference's method it returns a host array. */
+int agym_estimate_ctr(agym_handle* h, int32_t run, int32_t agent, const double* context, int32_t sample, const float* eps, uint64_t seed,
+                      int32_t iter, int64_t query, double* out, void* stream);
+
 /* Number of kernels of this library launched through this handle so far (bench.py's gpu_launches is a difference of
  * two readings; the reference has no counterpart: it launches nothing). */
 uint64_t agym_launch_count(const agym_handle* h);

@@ -205,3 +205,106 @@ def test_shards_reproduce_the_single_device_job(tmp_path, cfg, monkeypatch):
         parts = [driver.run_experiment(path, rank=r, world=world) for r in range(world)]
         np.testing.assert_array_equal(np.concatenate([p["metrics"] for p in parts]), whole["metrics"], err_msg=f"{cfg} world {world}")
         np.testing.assert_array_equal(np.concatenate([p["revenue"] for p in parts]), whole["revenue"], err_msg=f"{cfg} world {world}")
+
+
+def _surface_from_case(case):
+    """Reference-named objects (Agent / allocator / bidder / Auction) over a golden case's catalog and learnt state."""
+    import auction_gym_b200 as ag
+    from auction_gym_b200 import _lib
+    from oracle import auction_oracle as ao
+
+    rng = np.random.default_rng(0)
+    A, I, D, Do = int(case["A"]), int(case["I"]), int(case["D"]), int(case["Do"])
+    agents, a2i, a2v = [], {}, {}
+    for a in range(A):
+        n = int(case["n_items"][a])
+        name = f"agent {a}"
+        a2i[name], a2v[name] = case["E"][a, :n], case["V"][a, :n]
+        alloc = ag.OracleAllocator(rng) if case["alloc_kind"][a] == ao.ALLOC_ORACLE else \
+            ag.PyTorchLogisticRegressionAllocator(rng, Do, n, thompson_sampling=bool(case["alloc_kind"][a] == ao.ALLOC_TS))
+        agents.append(ag.Agent(rng, name, n, a2v[name], alloc, ag.TruthfulBidder(rng)))
+        if isinstance(alloc, ag.OracleAllocator):
+            alloc.update_item_embeddings(a2i[name])
+    mech = ag.SecondPrice() if case["mechanism"] == ao.MECH_SECOND else ag.FirstPrice()
+    auction = ag.Auction(rng, mech, agents, a2i, a2v, 1, D, float(case["embedding_var"]), Do, int(case["P"]), precision=_lib.FP64, seed=3)
+    auction._build()
+    if auction.engine.any_learnt:
+        auction.engine.set_allocator_state(case["m"][None], case["q"][None])
+    return auction
+
+
+@pytest.mark.parametrize("name", ["rounds_sp_ts", "rounds_sp_oracle", "rounds_sp_ts_64x64"])
+def test_per_context_methods_replay_the_reference(name):
+    """Allocator.estimate_CTR / Agent.select_item / Agent.bid for ONE context (BidderAllocation.py:67-68,81-82; Agent.py:29-68),
+    fed the golden rounds' contexts and Thompson noise: the chosen item is the reference's, the MAP estimate and the truthful
+    bid match to float32 rounding."""
+    _need_gpu()
+    from tests.conftest import load_golden
+
+    case, inp, ref, met = load_golden(name)
+    auction = _surface_from_case(case)
+    D, Do = int(case["D"]), int(case["Do"])
+    T = min(len(inp["ctx"]), 48)
+    for t in range(T):
+        true_ctx = np.concatenate([inp["ctx"][t, :D], [1.0]])
+        obs_ctx = np.concatenate([inp["ctx"][t, :Do], [1.0]])
+        for s, a in enumerate(inp["parts"][t]):
+            agent = auction.agents[int(a)]
+            oracle = type(agent.allocator).__name__ == "OracleAllocator"
+            ctx = true_ctx if oracle else obs_ctx
+            eps = None if oracle else inp["ts_eps"][t, s]
+            item, est = agent.select_item(ctx, _eps=eps)
+            assert item == int(ref["item"][t, s]), (t, s)
+            np.testing.assert_allclose(est, ref["est"][t, s], rtol=1e-12 if oracle else 2e-6, err_msg=str((t, s)))
+            assert np.asarray(est).dtype == (np.float64 if oracle else np.float32)  # the reference's mix (SURVEY.md section 0.7)
+            bid, item2 = agent.bid(ctx, _eps=eps)
+            assert item2 == item
+            np.testing.assert_allclose(bid, ref["bid"][t, s], rtol=1e-12 if oracle else 2e-6)
+            if not oracle:  # MAP estimates are deterministic; sampled ones differ between two draws
+                e1, e2 = agent.allocator.estimate_CTR(ctx, sample=False), agent.allocator.estimate_CTR(ctx, sample=False)
+                assert np.array_equal(e1, e2) and e1.shape == (agent.num_items,)
+                s1, s2 = agent.allocator.estimate_CTR(ctx), agent.allocator.estimate_CTR(ctx)
+                assert bool(agent.allocator.thompson_sampling) == (not np.array_equal(s1, s2))
+    auction.engine.close()
+
+
+def test_per_context_shaded_bid_follows_the_bidder_state(tmp_path):
+    """Bidder.bid for one opportunity (Bidder.py:171-179): before the first fit gamma ~ N(prev_gamma, gamma_sigma), bid = gamma x value x CTR."""
+    _need_gpu()
+    import auction_gym_b200 as ag
+
+    path = _small_config(tmp_path, "FP_DM_Oracle")
+    rng, config, agent_configs, E, V, num_runs, max_slots, D, var, Do = ag.parse_config(path)
+    agents = ag.instantiate_agents(rng, agent_configs, V, E)
+    auction, *_ = ag.instantiate_auction(rng, config, E, V, agents, max_slots, D, var, Do)
+    shaded = [a for a in auction.agents if not a.bidder.truthful][0]
+    gam = []
+    for _ in range(64):
+        b = shaded.bidder.bid(1.25, None, 0.2)
+        gam.append(b / (1.25 * 0.2))
+    gam = np.array(gam)
+    assert abs(gam.mean() - shaded.bidder.prev_gamma) < 5 * shaded.bidder.gamma_sigma / 8 and 0.3 * shaded.bidder.gamma_sigma < gam.std() < 2 * shaded.bidder.gamma_sigma
+    auction.engine.close()
+
+
+@pytest.mark.parametrize("cfg,over", [("SP_Truthful_TS", {}), ("FP_DR_TS", {}), ("SP_Truthful_TS", {"memory": 300})])
+def test_resume_from_checkpoint_equals_the_uninterrupted_job(tmp_path, cfg, over, monkeypatch):
+    """Per-iteration checkpoint of the learnt state: stop after two of four iterations, resume in a
+    fresh process-equivalent (new engine), and get the uninterrupted job's metrics bit for bit."""
+    _need_gpu()
+    from auction_gym_b200 import driver
+
+    cfgd = json.load(open(os.path.join(ROOT, "config", cfg + ".json")))
+    if "memory" in over:
+        for a in cfgd["agents"]:
+            a["memory"] = over["memory"]
+    cfgd.update(num_runs=3, num_iter=4, rounds_per_iter=600, output_dir=str(tmp_path / "out") + "/")
+    path = str(tmp_path / "cfg.json")
+    json.dump(cfgd, open(path, "w"))
+    whole = driver.run_experiment(path)
+    ck = str(tmp_path / "ck")
+    part = driver.run_experiment(path, checkpoint_dir=ck, stop_after=2)
+    np.testing.assert_array_equal(part["metrics"], whole["metrics"][:, :2])
+    rest = driver.run_experiment(path, checkpoint_dir=ck, resume=True)
+    np.testing.assert_array_equal(rest["metrics"], whole["metrics"])
+    np.testing.assert_array_equal(rest["revenue"], whole["revenue"])
