@@ -17,7 +17,7 @@ BID_ROW = 5
 TERM_ROW = 8         # AGYM_TERM_ROW
 FIT_ADAM_REF, FIT_ADAM_FAST = 0, 1
 (BFIT_NONE, BFIT_VL_SEARCH, BFIT_VL_POLICY, BFIT_PL_REINFORCE, BFIT_PL_OFFPOLICY, BFIT_PL_TRPO, BFIT_PL_PPO, BFIT_DR, BFIT_EMPIRICAL) = range(9)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enum mirrors (include/agym.h)
 SECOND_PRICE, FIRST_PRICE = 0, 1
@@ -35,7 +35,7 @@ class AgymError(RuntimeError):
 class Shape(C.Structure):
     _fields_ = [("R", C.c_int32), ("A", C.c_int32), ("I", C.c_int32), ("D", C.c_int32), ("Do", C.c_int32),
                 ("P", C.c_int32), ("mechanism", C.c_int32), ("precision", C.c_int32), ("run_offset", C.c_int32),
-                ("reserved", C.c_int32), ("embedding_var", C.c_double)]
+                ("max_slots", C.c_int32), ("embedding_var", C.c_double)]
 
 
 _LOG_FIELDS = ["agent", "item", "est", "value", "bid", "true_ctr", "best_ev", "price", "second", "gamma",
@@ -48,7 +48,7 @@ class RoundLog(C.Structure):
 
 class ReplayInputs(C.Structure):
     _fields_ = [("ctx", C.c_void_p), ("parts", C.c_void_p), ("ts_eps", C.c_void_p), ("gamma_z", C.c_void_p),
-                ("grid_u", C.c_void_p), ("u", C.c_void_p), ("grid_n", C.c_int32), ("reserved", C.c_int32)]
+                ("grid_u", C.c_void_p), ("u", C.c_void_p), ("grid_n", C.c_int32), ("reserved", C.c_int32), ("num_slots", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/agym.h declares

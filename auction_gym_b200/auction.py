@@ -22,8 +22,8 @@ class Auction:
     def __init__(self, rng, allocation, agents, agent2items, agents2item_values, max_slots, embedding_size, embedding_var,
                  obs_embedding_size, num_participants_per_round, *, num_runs=1, run_offset=0, device=0, precision=None,
                  seed=None, init_seed=None, rounds_capacity=0, per_run_init=None):
-        if max_slots != 1:
-            raise NotImplementedError("multi-slot auctions are not supported (src/main.py:36-37 says the same of the reference)")
+        if int(max_slots) < 1:
+            raise ValueError("max_slots must be >= 1")
         self.rng = rng
         self.allocation = allocation
         self.agents = agents
@@ -77,7 +77,7 @@ class Auction:
                      alloc_kind=[ag.allocator.kind for ag in self.agents], bidder_kind=[ag.bidder.kind for ag in self.agents],
                      embedding_var=float(self.embedding_var), precision=self.precision, device=self.device,
                      run_offset=self.run_offset, rounds_capacity=self._rounds_capacity,
-                     bidder_fit=[ag.bidder.fit_kind for ag in self.agents],
+                     bidder_fit=[ag.bidder.fit_kind for ag in self.agents], max_slots=int(self.max_slots),
                      memory=[int(ag.memory or 0) for ag in self.agents])
         if eng.any_learnt:
             m = np.zeros((self.num_runs, A, I, Do + 1), np.float32)

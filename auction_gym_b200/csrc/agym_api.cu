@@ -25,6 +25,7 @@ SimParams make_params(const agym_handle* h) {
   const agym_shape& s = h->shape;
   p.R = s.R; p.A = s.A; p.I = s.I; p.D = s.D; p.Do = s.Do; p.K = h->K; p.P = s.P;
   p.mechanism = s.mechanism;
+  p.max_slots = s.max_slots > 1 ? s.max_slots : 1;
   p.run_offset = s.run_offset;
   p.embedding_var = s.embedding_var;
   p.n_items = h->d_n_items; p.alloc_kind = h->d_alloc_kind; p.bidder_kind = h->d_bidder_kind;
@@ -72,6 +73,7 @@ int agym_create(const agym_shape* shape, int device, agym_handle** out) {
   if (s.A > 4096 || s.I > 4096) return set_error(nullptr, AGYM_ERR_INVALID, "agym_create: A and I are limited to 4096 (fit_meta packing)");
   if (s.mechanism != AGYM_SECOND_PRICE && s.mechanism != AGYM_FIRST_PRICE) return set_error(nullptr, AGYM_ERR_INVALID, "agym_create: unknown mechanism");
   if (s.precision != AGYM_FP32 && s.precision != AGYM_FP64) return set_error(nullptr, AGYM_ERR_INVALID, "agym_create: unknown precision");
+  if (s.max_slots < 0 || s.max_slots > kMaxP) return set_error(nullptr, AGYM_ERR_INVALID, "agym_create: max_slots must be in [0, 32]");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -295,7 +297,9 @@ int agym_simulate_rounds(agym_handle* h, uint64_t seed, int32_t iter, int64_t T,
   if (T < 0) return set_error(h, AGYM_ERR_INVALID, "agym_simulate_rounds: T < 0");
   int rc = ready_for_rounds(h, "agym_simulate_rounds");
   if (rc) return rc;
-  if (h->any_learnt && h->fit_ctx && h->log_base + h->rounds_in_iter + T > h->Tcap)
+  const int64_t S = h->shape.max_slots > 1 ? h->shape.max_slots : 1;  // winner-log rows per round
+  if (S > 1 && h->log_base > 0) return set_error(h, AGYM_ERR_UNSUPPORTED, "several slots per round together with log retention (Agent memory) is not built");
+  if (h->any_learnt && h->fit_ctx && h->log_base + (h->rounds_in_iter + T) * S > h->Tcap)
     return set_error(h, AGYM_ERR_INVALID, "agym_simulate_rounds: fit log capacity exceeded (call agym_clear_iteration or bind a larger log)");
   if (h->bid_rows && h->log_base + h->rounds_in_iter + T > h->bid_Tcap)
     return set_error(h, AGYM_ERR_INVALID, "agym_simulate_rounds: bid log capacity exceeded");
@@ -317,7 +321,9 @@ int agym_replay_rounds(agym_handle* h, int32_t run0, int32_t n_runs, int64_t T, 
   if (rc) return rc;
   if (h->any_shaded && !in->gamma_z && !(h->any_search && in->grid_u && in->grid_n > 0))
     return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: shaded bidders need gamma_z (and grid_u once a win-rate model is fitted)");
-  if (h->fit_ctx && h->log_base + h->rounds_in_iter + T > h->Tcap) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: fit log capacity exceeded");
+  const int64_t S = h->shape.max_slots > 1 ? h->shape.max_slots : 1;  // winner-log rows per round
+  if (S > 1 && h->log_base > 0) return set_error(h, AGYM_ERR_UNSUPPORTED, "several slots per round together with log retention (Agent memory) is not built");
+  if (h->fit_ctx && h->log_base + (h->rounds_in_iter + T) * S > h->Tcap) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: fit log capacity exceeded");
   if (h->bid_rows && h->log_base + h->rounds_in_iter + T > h->bid_Tcap) return set_error(h, AGYM_ERR_INVALID, "agym_replay_rounds: bid log capacity exceeded");
   // (the 128-point search grid grid_u is only read once some win-rate model is initialised)
   if (T == 0) return AGYM_OK;

@@ -30,6 +30,7 @@ __host__ __device__ inline int meta_item(uint32_t m) { return int(m & 0xFFFu); }
 // Everything a round-loop kernel needs, passed by value.
 struct SimParams {
   int R, A, I, D, Do, K, P, mechanism;
+  int max_slots;     // >= 1; rows of the winner log per round
   int run_offset;
   double embedding_var;
   // static per-agent configuration [A]
@@ -73,7 +74,7 @@ struct SimParams {
 // Philox4x32-10 (Salmon et al., SC'11), counter-based: key = (seed, run), counter = (round, iter,
 // purpose|slot, index).  Written out here; no curand dependency.
 // ------------------------------------------------------------------------------------------------
-enum Purpose : uint32_t { kPurposeCtx = 0, kPurposePart = 1, kPurposeClick = 2, kPurposeTS = 3, kPurposeGamma = 4, kPurposeGrid = 5 };
+enum Purpose : uint32_t { kPurposeCtx = 0, kPurposePart = 1, kPurposeClick = 2, kPurposeTS = 3, kPurposeGamma = 4, kPurposeGrid = 5, kPurposeSlots = 6 };
 
 struct PhiloxKey {
   uint32_t k0, k1;

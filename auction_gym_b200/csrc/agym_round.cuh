@@ -318,6 +318,15 @@ __device__ __forceinline__ uint32_t click_word(RoundCounter rc, PhiloxKey key) {
   const int j = int(rc.round & 3);
   return j == 0 ? w.x : j == 1 ? w.y : j == 2 ? w.z : w.w;
 }
+// several slots per round (Auction.py:30,65): slot k > 0 takes its click uniform from its own Philox block, and the
+// number of slots of the round is uniform in [1, max_slots]
+__device__ __forceinline__ uint32_t click_word_slot(RoundCounter rc, PhiloxKey key, int slot) {
+  if (slot == 0) return click_word(rc, key);
+  return philox4x32_10(rc.c0, rc.c1, kPurposeClick << 16, uint32_t(slot), key).x;
+}
+__device__ __forceinline__ int draw_num_slots(int max_slots, RoundCounter rc, PhiloxKey key) {
+  return 1 + int(philox4x32_10(rc.c0, rc.c1, kPurposeSlots << 16, 0u, key).x % uint32_t(max_slots));
+}
 __device__ __forceinline__ float click_uniform_f(RoundCounter rc, PhiloxKey key) { return u32_to_unit(click_word(rc, key)); }
 __device__ __forceinline__ double click_uniform_d(RoundCounter rc, PhiloxKey key) {
   return (double(click_word(rc, key)) + 0.5) * (1.0 / 4294967296.0);

@@ -14,7 +14,7 @@
 
 namespace agym {
 
-template <typename Real, int G, int DMAX, bool kReplay, int DT, int DoT>
+template <typename Real, int G, int DMAX, bool kReplay, int DT, int DoT, bool kMulti>
 __global__ void __launch_bounds__(256, DT > 0 ? 3 : 1) sim_kernel(const SimParams p, const agym_replay_inputs in, const agym_round_log log) {
   using A_ = Arith<Real>;
   const int lane = threadIdx.x % G, group = threadIdx.x / G, ngroups = blockDim.x / G;
@@ -84,39 +84,86 @@ __global__ void __launch_bounds__(256, DT > 0 ? 3 : 1) sim_kernel(const SimParam
       }
     }
 
-    // ---- resolution + click (AuctionAllocation.py:18-35, Auction.py:60-65) ----
+    // ---- resolution + click (AuctionAllocation.py:18-35, Auction.py:60-74) ----
+    // per participant (lane < P): did it win a slot, what was it charged, what does its log record say afterwards
     const bool valid = P >= 2;  // P == 1: the reference's price array is empty and nobody is charged
-    const Real price = valid ? (p.mechanism == AGYM_FIRST_PRICE ? best : second) : Real(0);
-    const Real second_p = valid ? second : Real(0);
-    const Real tw = shfl_idx<G>(r_true, wslot);
-    Real u;
-    if (kReplay) u = Real(in.u[ri]);
-    else u = sizeof(Real) == 8 ? Real(click_uniform_d(rc, key)) : Real(click_uniform_f(rc, key));
-    const bool click = valid && (u < tw);
-    const int w_agent = shfl_idx<G>(my_agent, wslot);
-    const int w_item = shfl_idx<G>(r_item, wslot);
+    const int S = kMulti ? p.max_slots : 1;  // rows of the winner log per round (kMulti: a separate instantiation, the single-slot hot path pays nothing)
+    bool won_me = false, clk_me = false;
+    Real paid_me = 0, sec_me = 0, logged_price = 0;
+    int top_slot = wslot, my_rank = 0, n_charged = valid ? 1 : 0;
+    if (S <= 1) {
+      const Real price = valid ? (p.mechanism == AGYM_FIRST_PRICE ? best : second) : Real(0);
+      const Real tw = shfl_idx<G>(r_true, wslot);
+      Real u;
+      if (kReplay) u = Real(in.u[ri]);
+      else u = sizeof(Real) == 8 ? Real(click_uniform_d(rc, key)) : Real(click_uniform_f(rc, key));
+      won_me = valid && lane == wslot;
+      clk_me = won_me && (u < tw);
+      paid_me = price;
+      sec_me = valid ? second : Real(0);
+      logged_price = price;
+      my_rank = won_me ? 0 : 1;
+    } else {
+      // Several slots (Auction.py:30,60-74; AuctionAllocation.py:19-23,33-35): slot k goes to the k-th highest bid (equal
+      // bids keep slot order), price_k = sorted[k] (first price) or sorted[k + 1] (second price), second_k = sorted[k + 1].
+      // The reference zips winners, prices and second_prices, so only min(num_slots, P - 1) slots are charged.  Every
+      // slot's set_price overwrites the logged price of all the others: afterwards every participant's record holds the
+      // LAST slot's price, while utilities and revenue were charged slot by slot.
+      const int ns = kReplay ? (in.num_slots ? in.num_slots[ri] : 1) : draw_num_slots(S, rc, key);
+      n_charged = min(ns, P - 1);
+      const Real my_bid = lane < P ? r_bid : A_::neg_inf();
+      for (int j2 = 0; j2 < P; ++j2) {
+        const Real bj = shfl_idx<G>(my_bid, j2);
+        my_rank += (bj > my_bid) || (bj == my_bid && j2 < lane);
+      }
+      const int shift = p.mechanism == AGYM_FIRST_PRICE ? 0 : 1;
+      for (int j2 = 0; j2 < P; ++j2) {  // sorted[q] = the bid of the participant ranked q
+        const Real bj = shfl_idx<G>(my_bid, j2);
+        const int rj = shfl_idx<G>(my_rank, j2);
+        if (rj == my_rank + shift) paid_me = bj;
+        if (rj == my_rank + 1) sec_me = bj;
+        if (rj == n_charged - 1 + shift) logged_price = bj;
+        if (rj == 0) top_slot = j2;
+      }
+      if (n_charged < 1) logged_price = Real(0);
+      won_me = lane < P && my_rank < n_charged;
+      if (won_me) {
+        Real u;
+        if (kReplay) u = Real(in.u[ri * S + my_rank]);
+        else u = sizeof(Real) == 8 ? (Real(click_word_slot(rc, key, my_rank)) + Real(0.5)) * Real(1.0 / 4294967296.0)
+                                   : Real(u32_to_unit(click_word_slot(rc, key, my_rank)));
+        clk_me = u < r_true;
+      } else {
+        sec_me = Real(0);
+      }
+    }
+    // the winner of the first slot: what the single-slot winner record is made of
+    const bool click = shfl_idx<G>(int(clk_me), top_slot) != 0;
+    const int w_agent = shfl_idx<G>(my_agent, top_slot);
+    const int w_item = shfl_idx<G>(r_item, top_slot);
 
     if (active) {
       // ---- charge / set_price and metric sums (Agent.py:70-118) ----
-      const long long tl = ta + p.log_base;  // row in the winner / bid logs (retained records sit in front)
+      const long long tl = ta + p.log_base;  // row in the bid log (retained records sit in front)
       if (lane < P) {
-        const bool won = valid && lane == wslot;
+        const bool won = won_me;
         const Real tv = r_true * r_val;
         double* __restrict__ ac = p.acc + ((size_t)run * A + my_agent) * kNumMetrics;
         const Real de = r_true - r_est;
         const double t_alloc = double(r_bev - tv), t_estim = double(r_est * r_val - tv), t_sq = double(de * de);
         double t_over = 0.0, t_under = 0.0, t_bias = 0.0;
         if (won) {
-          const Real got = click ? r_val : Real(0);
-          t_over = double(price - second_p);
+          const Real got = clk_me ? r_val : Real(0);
+          t_over = double(logged_price - sec_me);
           t_bias = double(r_est / r_true);
-          atomicAdd(ac + AGYM_M_NET, double(got - price));
+          atomicAdd(ac + AGYM_M_NET, double(got - paid_me));
           atomicAdd(ac + AGYM_M_GROSS, double(got));
           atomicAdd(ac + AGYM_M_OVERBID_REGRET, t_over);
           atomicAdd(ac + AGYM_M_BIAS, t_bias);
           atomicAdd(ac + AGYM_M_NWON, 1.0);
-        } else if (price < tv) {
-          t_under = double(price - r_bid);
+          if (S > 1) atomicAdd(p.revenue + run, double(paid_me));  // Auction.py:74, once per charged slot
+        } else if (logged_price < tv) {  // nobody charged (P == 1): the logged price stays 0 (Impression.py), the getter still counts it
+          t_under = double(logged_price - r_bid);
           atomicAdd(ac + AGYM_M_UNDERBID_REGRET, t_under);
         }
         atomicAdd(ac + AGYM_M_ALLOC_REGRET, t_alloc);
@@ -134,29 +181,45 @@ __global__ void __launch_bounds__(256, DT > 0 ? 3 : 1) sim_kernel(const SimParam
           tr[3] = make_double2(r_gamma == r_gamma ? double(r_gamma) : 0.0, double(r_bev));
         }
       }
-      if (lane == 0 && valid) atomicAdd(p.revenue + run, double(price));  // Auction.py:74
+      if (S <= 1 && lane == 0 && valid) atomicAdd(p.revenue + run, double(logged_price));  // Auction.py:74
 
-      // ---- winner record for the allocator fit (Agent.py:81-91: won rows only) ----
-      if (p.fit_ctx != nullptr && tl < p.Tcap) {
-        const size_t fi = (size_t)run * p.Tcap + tl;
+      // ---- winner records for the allocator fit (Agent.py:81-91: won rows only), S rows per round ----
+      if (p.fit_ctx != nullptr) {
+        if (S <= 1) {
+          if (tl < p.Tcap) {
+            const size_t fi = (size_t)run * p.Tcap + tl;
 #pragma unroll
-        for (int k = 0; k < DMAX; ++k)
-          if (k < Do && lane == (k % G)) p.fit_ctx[fi * Do + k] = float(ctx[k]);
-        if (lane == 0) p.fit_meta[fi] = valid ? pack_meta(w_agent, w_item, click) : 0u;
+            for (int k = 0; k < DMAX; ++k)
+              if (k < Do && lane == (k % G)) p.fit_ctx[fi * Do + k] = float(ctx[k]);
+            if (lane == 0) p.fit_meta[fi] = valid ? pack_meta(w_agent, w_item, click) : 0u;
+          }
+        } else {
+          const long long row0 = p.log_base + ta * S;
+          if (row0 + S <= p.Tcap) {
+            const size_t f0 = (size_t)run * p.Tcap + row0;
+            if (won_me) {  // the winner of slot my_rank writes that slot's row
+#pragma unroll
+              for (int k = 0; k < DMAX; ++k)
+                if (k < Do) p.fit_ctx[(f0 + my_rank) * Do + k] = float(ctx[k]);
+              p.fit_meta[f0 + my_rank] = pack_meta(my_agent, r_item, clk_me);
+            }
+            if (lane < S && lane >= n_charged) p.fit_meta[f0 + lane] = 0u;  // slots nobody was charged for
+          }
+        }
       }
 
       // ---- bid records for the bidder fits (Agent.py:81-94: bidder.update sees every row) ----
       if (p.bid_rows != nullptr && tl < p.bid_Tcap && lane < P) {
-        const bool won = valid && lane == wslot;
+        const bool won = won_me;
         const size_t bi = ((size_t)run * p.bid_Tcap + tl) * P + lane;
         float* __restrict__ row = p.bid_rows + bi * AGYM_BID_ROW;
-        row[0] = float(r_est); row[1] = float(r_val); row[2] = float(r_gamma); row[3] = float(r_prop); row[4] = float(price);
-        p.bid_meta[bi] = kBidValid | (won ? kBidWon : 0u) | ((won && click) ? kBidClick : 0u) | (uint32_t(r_item) << 12) | uint32_t(my_agent);
+        row[0] = float(r_est); row[1] = float(r_val); row[2] = float(r_gamma); row[3] = float(r_prop); row[4] = float(logged_price);
+        p.bid_meta[bi] = kBidValid | (won ? kBidWon : 0u) | ((won && clk_me) ? kBidClick : 0u) | (uint32_t(r_item) << 12) | uint32_t(my_agent);
       }
 
       // ---- detailed log (Impression.py:4-31); `has_log` spares the production launch the per-field null checks ----
       if (has_log && lane < P) {
-        const bool won = valid && lane == wslot;
+        const bool won = won_me;
         const size_t li = (size_t)ri * P + lane;
         if (log.agent) log.agent[li] = my_agent;
         if (log.item) log.item[li] = r_item;
@@ -165,15 +228,15 @@ __global__ void __launch_bounds__(256, DT > 0 ? 3 : 1) sim_kernel(const SimParam
         if (log.bid) log.bid[li] = double(r_bid);
         if (log.true_ctr) log.true_ctr[li] = double(r_true);
         if (log.best_ev) log.best_ev[li] = double(r_bev);
-        if (log.price) log.price[li] = double(price);
-        if (log.second) log.second[li] = won ? double(second_p) : 0.0;
+        if (log.price) log.price[li] = double(logged_price);
+        if (log.second) log.second[li] = won ? double(sec_me) : 0.0;
         if (log.gamma) log.gamma[li] = double(r_gamma);
         if (log.propensity) log.propensity[li] = double(r_prop);
-        if (log.outcome) log.outcome[li] = (won && click) ? 1 : 0;
+        if (log.outcome) log.outcome[li] = (won && clk_me) ? 1 : 0;
         if (log.won) log.won[li] = won ? 1 : 0;
       }
       if (has_log && lane == 0) {
-        if (log.winner) log.winner[ri] = wslot;
+        if (log.winner) log.winner[ri] = top_slot;
         if (log.ctx) {
 #pragma unroll
           for (int d = 0; d < DMAX; ++d)
@@ -214,14 +277,19 @@ static int launch_g(agym_handle* h, const SimParams& p, const agym_replay_inputs
   if (log) lg = *log;
   agym_replay_inputs ri = {};
   const bool std_shape = DMAX == 8 && p.D == 5 && p.Do == 4;  // every shipped config and the bench shape
+#define AGYM_SIM(REPLAY, MULTI)                                                                                                   \
+  do {                                                                                                                            \
+    if (std_shape) sim_kernel<Real, G, DMAX, REPLAY, (DMAX == 8 ? 5 : 0), (DMAX == 8 ? 4 : 0), MULTI><<<unsigned(grid), threads, 0, s>>>(q, ri, lg); \
+    else sim_kernel<Real, G, DMAX, REPLAY, 0, 0, MULTI><<<unsigned(grid), threads, 0, s>>>(q, ri, lg);                             \
+  } while (0)
+  const bool multi = p.max_slots > 1;
   if (in) {
     ri = *in;
-    if (std_shape) sim_kernel<Real, G, DMAX, true, (DMAX == 8 ? 5 : 0), (DMAX == 8 ? 4 : 0)><<<unsigned(grid), threads, 0, s>>>(q, ri, lg);
-    else sim_kernel<Real, G, DMAX, true, 0, 0><<<unsigned(grid), threads, 0, s>>>(q, ri, lg);
+    if (multi) AGYM_SIM(true, true); else AGYM_SIM(true, false);
   } else {
-    if (std_shape) sim_kernel<Real, G, DMAX, false, (DMAX == 8 ? 5 : 0), (DMAX == 8 ? 4 : 0)><<<unsigned(grid), threads, 0, s>>>(q, ri, lg);
-    else sim_kernel<Real, G, DMAX, false, 0, 0><<<unsigned(grid), threads, 0, s>>>(q, ri, lg);
+    if (multi) AGYM_SIM(false, true); else AGYM_SIM(false, false);
   }
+#undef AGYM_SIM
   h->launches += 1;
   return check_cuda(h, cudaGetLastError(), "sim_kernel launch");
 }

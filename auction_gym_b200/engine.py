@@ -35,16 +35,17 @@ class Engine:
     """
 
     def __init__(self, *, R, A, I, D, Do, P, mechanism, E, V, n_items, alloc_kind, bidder_kind, embedding_var=1.0,
-                 precision=_lib.FP32, device=0, run_offset=0, rounds_capacity=0, bidder_fit=None, memory=None):
+                 precision=_lib.FP32, device=0, run_offset=0, rounds_capacity=0, bidder_fit=None, memory=None, max_slots=1):
         if not torch.cuda.is_available():
             raise AgymError("CUDA device required: the AuctionGym B200 engine has no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device("cuda", device)
         self.R, self.A, self.I, self.D, self.Do, self.P = int(R), int(A), int(I), int(D), int(Do), int(P)
         self.K = self.Do + 1
+        self.max_slots = max(1, int(max_slots))  # slots per round are uniform in [1, max_slots] (Auction.py:30)
         self.mechanism, self.precision = int(mechanism), int(precision)
         self.shape = Shape(self.R, self.A, self.I, self.D, self.Do, self.P, self.mechanism, self.precision,
-                           int(run_offset), 0, float(embedding_var))
+                           int(run_offset), self.max_slots, float(embedding_var))
         self.handle = C.c_void_p()
         rc = self.lib.agym_create(C.byref(self.shape), device, C.byref(self.handle))
         if rc != 0:
@@ -138,8 +139,8 @@ class Engine:
         done = int(self.lib.agym_rounds_in_iteration(self.handle))
         if done:  # growing in the middle of an iteration (simulate_opportunity() one round at a time): amortise
             T = max(T, 2 * self.rounds_capacity)
-        dev, cap = self.device, T + self.log_base
-        filled = self.log_base + done  # retained rows + rounds recorded so far move to the new buffers
+        dev, cap = self.device, T * self.max_slots + self.log_base  # the winner log holds max_slots rows per round
+        filled = self.log_base + done * self.max_slots  # retained rows + rounds recorded so far move to the new buffers
 
         def grown(old, shape, dtype, zero):
             new = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
@@ -264,16 +265,23 @@ class Engine:
                                                   C.byref(log) if log is not None else None, self._stream()))
         return out
 
-    def replay(self, ctx, parts, u, ts_eps=None, gamma_z=None, grid_u=None, run0=0, log_fields=tuple(_lib._LOG_FIELDS[:-1])):
-        """Replay mode: host-drawn noise for runs ``[run0, run0 + n_runs)``; inputs have a leading run axis."""
+    def replay(self, ctx, parts, u, ts_eps=None, gamma_z=None, grid_u=None, run0=0, log_fields=tuple(_lib._LOG_FIELDS[:-1]), num_slots=None):
+        """Replay mode: host-drawn noise for runs ``[run0, run0 + n_runs)``; inputs have a leading run axis.
+        With ``max_slots`` > 1: ``u`` is [n_runs, T, max_slots] and ``num_slots`` [n_runs, T] (Auction.py:30,65)."""
         dev = self.device
         ctx = torch.as_tensor(np.ascontiguousarray(ctx, np.float64)).to(dev)
         n_runs, T = ctx.shape[0], ctx.shape[1]
         parts_t = torch.as_tensor(np.ascontiguousarray(parts, np.int32)).to(dev)
         u_t = torch.as_tensor(np.ascontiguousarray(u, np.float64)).to(dev)
-        assert ctx.shape == (n_runs, T, self.D) and parts_t.shape == (n_runs, T, self.P) and u_t.shape == (n_runs, T)
+        assert ctx.shape == (n_runs, T, self.D) and parts_t.shape == (n_runs, T, self.P)
+        assert u_t.shape == ((n_runs, T) if self.max_slots == 1 else (n_runs, T, self.max_slots)), u_t.shape
         keep = [ctx, parts_t, u_t]
-        rin = ReplayInputs(ctx.data_ptr(), parts_t.data_ptr(), None, None, None, u_t.data_ptr(), 0, 0)
+        rin = ReplayInputs(ctx.data_ptr(), parts_t.data_ptr(), None, None, None, u_t.data_ptr(), 0, 0, None)
+        if num_slots is not None:
+            ns = torch.as_tensor(np.ascontiguousarray(num_slots, np.int32)).to(dev)
+            assert ns.shape == (n_runs, T) and self.max_slots > 1
+            keep.append(ns)
+            rin.num_slots = ns.data_ptr()
         if ts_eps is not None:
             e = torch.as_tensor(np.ascontiguousarray(ts_eps, np.float32)).to(dev)
             assert e.shape == (n_runs, T, self.P, self.I, self.K), e.shape

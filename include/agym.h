@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AGYM_ABI_VERSION 1
+#define AGYM_ABI_VERSION 2
 
 typedef struct agym_handle agym_handle;
 
@@ -72,7 +72,8 @@ typedef struct agym_shape {
   int32_t precision;   /* agym_precision */
   int32_t run_offset;  /* global index of this device's first run: RNG keys use run_offset + r, so a
                           sharded job reproduces the single-device job (main.py:186) */
-  int32_t reserved;
+  int32_t max_slots;   /* slots per auction round are uniform in [1, max_slots] (Auction.py:30); 0 or 1 = the reference driver's
+                          single slot (main.py:36-37).  With several slots the winner log holds max_slots rows per round. */
   double embedding_var; /* used as the STD of the context normal, as Auction.py:33 does */
 } agym_shape;
 
@@ -116,9 +117,10 @@ typedef struct agym_replay_inputs {
   const float* ts_eps;    /* [n_runs][T][P][I][K] standard normals for Models.py:31, or NULL */
   const double* gamma_z;  /* [n_runs][T][P] standard normals for Bidder.py:177,354,461, or NULL */
   const double* grid_u;   /* [n_runs][T][P][grid_n] uniforms for Bidder.py:185, or NULL */
-  const double* u;        /* [n_runs][T] click uniforms: outcome = (u < p)        Auction.py:65 */
+  const double* u;        /* [n_runs][T][max_slots] click uniforms, one per slot: outcome = (u < p)   Auction.py:65 */
   int32_t grid_n;
   int32_t reserved;
+  const int32_t* num_slots; /* [n_runs][T] rng.integers(1, max_slots + 1) (Auction.py:30), or NULL = 1 slot; only read when max_slots > 1 */
 } agym_replay_inputs;
 
 /* every entry point below is exported even when the library is built with -fvisibility=hidden */

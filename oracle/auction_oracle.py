@@ -200,8 +200,63 @@ def resolve(bids, mechanism):
     return winner, price, second, np.ones(T, bool)
 
 
-def simulate_rounds(case, ctx, parts, u, ts_eps=None, gamma_z=None, grid_u=None):
+def resolve_slots(bids, mechanism, num_slots):
+    """AuctionAllocation.py:18-23,32-35 with num_slots [T] >= 1 (Auction.py:30,60-74; `max_slots` > 1).
+
+    Returns rank [T, P] (0 = highest bid; equal bids keep slot order: numpy's argsort of a handful of elements is an insertion
+    sort), srt [T, P] bids in descending order, K [T] = slots actually charged.  The reference zips winners, prices and
+    second_prices (Auction.py:68); second_prices = sorted[1 : num_slots + 1] has only P - 1 entries at most, and for
+    SecondPrice so has prices, so K = min(num_slots, P - 1): the slot whose runner-up does not exist is silently dropped.
+    """
+    T, P = bids.shape
+    order = np.argsort(-bids, axis=1, kind="stable")
+    rank = np.empty_like(order)
+    np.put_along_axis(rank, order, np.arange(P)[None, :], axis=1)
+    srt = np.take_along_axis(bids, order, axis=1)
+    K = np.minimum(np.asarray(num_slots, np.int64), P - 1)
+    return rank, srt, K
+
+
+def _finish_multislot(rec, parts, u, mechanism, num_slots, A):
+    """Charging with several slots per round (Auction.py:60-74, Agent.py:70-77).  Slot k's winner is charged price_k and
+    logs (price_k, second_k, outcome_k, won); every other participant's logged price is overwritten by set_price(price_k) --
+    so after the last slot EVERY participant's logged price is the last slot's price, while utilities were charged slot by
+    slot.  The log-derived regrets (Agent.py:104-112) therefore see the last price; net utility and revenue do not."""
+    T, P = parts.shape
+    rank, srt, K = resolve_slots(rec["bid"], mechanism, num_slots)
+    srt_pad = np.concatenate([srt, np.zeros((T, 1))], axis=1)
+    ar = np.arange(T)[:, None]
+    won = rank < K[:, None]
+    own_price = np.take_along_axis(srt_pad, rank + (0 if mechanism == MECH_FIRST else 1), axis=1)  # price of the slot the participant wins
+    own_second = np.take_along_axis(srt_pad, rank + 1, axis=1)
+    last = np.clip(K - 1, 0, None)
+    last_price = np.where(K > 0, srt_pad[np.arange(T), last + (0 if mechanism == MECH_FIRST else 1)], 0.0)
+    u2 = np.asarray(u, np.float64).reshape(T, -1)
+    uk = np.take_along_axis(u2, np.minimum(rank, u2.shape[1] - 1), axis=1)  # the click uniform of the slot the participant wins
+    outcome = won & (uk < rec["true_ctr"])
+    rec["rank"] = rank.astype(np.int32)
+    rec["won"] = won.astype(np.uint8)
+    rec["outcome"] = outcome.astype(np.uint8)
+    rec["price"] = np.broadcast_to(last_price[:, None], (T, P)).copy()
+    rec["second"] = np.where(won, own_second, 0.0)
+    rec["paid"] = np.where(won, own_price, 0.0)
+    rec["winner"] = np.argmin(rank, axis=1).astype(np.int32)
+    rec["n_charged"] = K.astype(np.int32)
+    srt2 = np.sort(rec["bid"], axis=1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        gaps = np.diff(srt2, axis=1) / np.maximum(np.abs(srt2[:, 1:]), 1e-300)
+    rec["bid_margin"] = np.nan_to_num(gaps.min(axis=1), nan=0.0) if P >= 2 else np.ones(T)
+    metrics = accumulate_metrics(rec, parts, A)
+    tv = rec["true_ctr"] * rec["value"]
+    flat = parts.ravel()
+    metrics["acc"][:, M_NET] = np.bincount(flat, weights=np.where(won, rec["value"] * outcome - rec["paid"], 0.0).ravel(), minlength=A)[:A]
+    metrics["revenue"] = np.float64(rec["paid"].sum())  # Auction.py:74: += price per charged slot
+    return rec, metrics
+
+
+def simulate_rounds(case, ctx, parts, u, ts_eps=None, gamma_z=None, grid_u=None, num_slots=None):
     """Vectorised restatement of T calls of Auction.simulate_opportunity (Auction.py:28-74).
+    ``num_slots`` [T] (with ``u`` [T, max_slots]) switches to several slots per round (Auction.py:30, `max_slots` > 1).
 
     ctx [T, D] f64 (already scaled by embedding_var), parts [T, P] int, u [T] f64 click uniforms,
     ts_eps [T, P, I, Do+1] f32, gamma_z [T, P] f64, grid_u [T, P, G] f64.
@@ -242,6 +297,8 @@ def simulate_rounds(case, ctx, parts, u, ts_eps=None, gamma_z=None, grid_u=None)
             rec["propensity"][rows, s] = prop
             rec["best_ev"][rows, s] = np.max(true_all * case["V"][a, :nI][None, :], axis=1)  # Auction.py:53
             rec["true_ctr"][rows, s] = true_all[np.arange(len(rows)), item]
+    if num_slots is not None:
+        return _finish_multislot(rec, parts, u, int(case["mechanism"]), num_slots, A)
     winner, price, second, valid = resolve(rec["bid"], int(case["mechanism"]))
     ar = np.arange(T)
     outcome = (u < rec["true_ctr"][ar, winner]) & valid  # Auction.py:65 (replay click rule)

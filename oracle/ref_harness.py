@@ -105,17 +105,19 @@ class ReplayRNG:
     u          [T]        uniforms; ``rng.binomial(1, p)`` -> (u[t] < p)           (Auction.py:65)
     """
 
-    def __init__(self, ctx, parts, u, gamma_z=None, grid_u=None):
+    def __init__(self, ctx, parts, u, gamma_z=None, grid_u=None, num_slots=None):
         self.ctx = np.asarray(ctx, dtype=np.float64)
         self.parts = np.asarray(parts, dtype=np.int64)
         self.u = np.asarray(u, dtype=np.float64)
         self.gamma_z = None if gamma_z is None else np.asarray(gamma_z, dtype=np.float64)
         self.grid_u = None if grid_u is None else np.asarray(grid_u, dtype=np.float64)
+        self.num_slots = None if num_slots is None else np.asarray(num_slots, dtype=np.int64)  # [T] for max_slots > 1 (Auction.py:30)
         self.t = -1
         self.slot = 0  # participant slot inside the current round; advanced by the bid wrapper
 
     def integers(self, lo, hi):
-        return 1
+        # Auction.py:30 draws the slot count BEFORE the context, i.e. before `t` advances
+        return 1 if self.num_slots is None else int(self.num_slots[self.t + 1])
 
     def normal(self, mu, sd, size=None):
         if size is not None:
@@ -131,7 +133,9 @@ class ReplayRNG:
         return lo + (hi - lo) * self.grid_u[self.t, self.slot, :size].copy()
 
     def binomial(self, n, p):
-        return (self.u[self.t] < np.asarray(p)).astype(np.int64)
+        p = np.asarray(p)
+        u = self.u[self.t]
+        return (u[: len(p)] < p).astype(np.int64) if np.ndim(u) else (u < p).astype(np.int64)
 
 
 class patched_ts_noise:
@@ -160,7 +164,7 @@ class patched_ts_noise:
         return False
 
 
-def build_reference_auction(cfg: dict, E: dict, V: dict, rng, ref=None):
+def build_reference_auction(cfg: dict, E: dict, V: dict, rng, ref=None, max_slots=1):
     """Instantiate the reference's agents + auction for ``cfg`` (same schema as config/*.json)
     through the reference's own helpers (src/main.py:77-109)."""
     ref = ref or load_reference()
@@ -181,7 +185,7 @@ def build_reference_auction(cfg: dict, E: dict, V: dict, rng, ref=None):
             n += 1
     agents = main.instantiate_agents(rng, agent_configs, V, E)
     auction, num_iter, rounds_per_iter, output_dir = main.instantiate_auction(
-        rng, cfg, E, V, agents, 1, cfg["embedding_size"], cfg["embedding_var"], cfg["obs_embedding_size"]
+        rng, cfg, E, V, agents, max_slots, cfg["embedding_size"], cfg["embedding_var"], cfg["obs_embedding_size"]
     )
     return auction, agents, agent_configs
 

@@ -34,7 +34,12 @@ def load_golden(name):
 
 
 def round_golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "rounds_*.npz")))
+    """Single-slot round goldens (the several-slots-per-round ones have their own tests: multislot_golden_names)."""
+    return sorted(n for n in (os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "rounds_*.npz"))) if "_slots" not in n)
+
+
+def multislot_golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "rounds_*_slots*.npz")))
 
 
 @pytest.fixture(scope="session")

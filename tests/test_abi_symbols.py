@@ -42,7 +42,7 @@ def test_ctypes_structs_match_header_layout():
     L = ag._lib
     assert C.sizeof(L.Shape) == 10 * 4 + 8
     assert C.sizeof(L.RoundLog) == 15 * C.sizeof(C.c_void_p)
-    assert C.sizeof(L.ReplayInputs) == 6 * C.sizeof(C.c_void_p) + 8
+    assert C.sizeof(L.ReplayInputs) == 7 * C.sizeof(C.c_void_p) + 8
     hdr = open(HEADER).read()
     enum = re.search(r"enum agym_metric \{(.*?)\}", hdr, flags=re.S).group(1)
     names = [n.strip().split("=")[0].strip() for n in enum.replace("\n", " ").split(",") if n.strip()]
@@ -102,4 +102,4 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                     "-L", libdir, "-lagym", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
-    assert out.startswith("1 -1 -1 agym_create")
+    assert out.startswith("2 -1 -1 agym_create")  # AGYM_ABI_VERSION 2: agym_replay_inputs.num_slots, agym_shape.max_slots

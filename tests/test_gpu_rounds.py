@@ -11,7 +11,7 @@ import pytest
 
 from oracle import auction_oracle as ao
 from tests import parity
-from tests.conftest import load_golden, round_golden_names
+from tests.conftest import load_golden, multislot_golden_names, round_golden_names
 
 pytestmark = pytest.mark.gpu
 
@@ -164,3 +164,94 @@ def test_abi_error_paths():
     with pytest.raises(ag.AgymError, match="bad run range"):
         eng.replay(inp["ctx"][None, :4], inp["parts"][None, :4], inp["u"][None, :4], run0=1)
     eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name", multislot_golden_names())
+def test_replay_multislot_matches_oracle_and_reference(name, precision):
+    """Several slots per round (Auction.py:30,60-74; AuctionAllocation.py:19-23,33-35) in the fused kernel against the oracle
+    and against the UNMODIFIED reference run with max_slots 2 / 3 (tests/golden/rounds_*_slots.npz): winners of every slot,
+    per-slot clicks, slot-by-slot charging, the log overwritten by the last slot's price, S winner-log rows per round."""
+    gu = _gpu()
+    import auction_gym_b200 as ag
+    from auction_gym_b200 import _lib
+
+    case, inp, ref, met = load_golden(name)
+    S = int(case["max_slots"])
+    A, I = int(case["A"]), int(case["I"])
+    eng = ag.Engine(R=1, A=A, I=I, D=int(case["D"]), Do=int(case["Do"]), P=int(case["P"]), mechanism=int(case["mechanism"]), E=case["E"], V=case["V"],
+                    n_items=case["n_items"], alloc_kind=[gu.ALLOC[int(k)] for k in case["alloc_kind"]],
+                    bidder_kind=[gu.BID[int(k)] for k in case["bidder_kind"]], embedding_var=float(case["embedding_var"]),
+                    precision=_lib.FP64 if precision == "fp64" else _lib.FP32, max_slots=S)
+    learnt = bool((case["alloc_kind"] != ao.ALLOC_ORACLE).any())
+    if learnt:
+        eng.set_allocator_state(case["m"][None], case["q"][None])
+    if eng.any_shaded:
+        eng.set_bidder_state(case["bidder_f"][:, 0][None, :], case["bidder_f"][:, 1][None, :])
+    kw = {}
+    if learnt:
+        kw["ts_eps"] = inp["ts_eps"][None]
+    if "gamma_z" in inp:
+        kw["gamma_z"] = inp["gamma_z"][None]
+    got = gu.log_to_numpy(eng.replay(inp["ctx"][None], inp["parts"][None], inp["u"][None], num_slots=inp["num_slots"][None], **kw))
+    rec, m = ao.simulate_rounds(case, inp["ctx"], inp["parts"], inp["u"], inp.get("ts_eps"), inp.get("gamma_z"), None, num_slots=inp["num_slots"])
+    T, P = inp["parts"].shape
+    exact = precision == "fp64"
+    # float32: a rank may flip only where two DIFFERENT bids are within float32 resolution (exactly equal bids stay equal)
+    srt = np.sort(rec["bid"], axis=1)
+    gaps = np.diff(srt, axis=1)
+    near = ((gaps > 0) & (gaps < 1e-5 * np.abs(srt[:, 1:]))).any(axis=1)
+    ok = np.ones(T, bool) if exact else ~near & (rec["item_margin"] > 1e-5).all(axis=1)
+    assert ok.mean() > 0.97
+    for want, who in ((rec, "oracle"), (ref, "reference")):
+        for k in ("item", "won", "outcome"):
+            assert np.array_equal(got[k][ok], np.asarray(want[k])[ok]), f"{name} {who}: {k}"
+        tol = (parity.RTOL_F32_EST if learnt else parity.RTOL_F64) if exact else 1e-5
+        for k in ("bid", "price", "second", "est", "true_ctr", "best_ev", "value"):
+            np.testing.assert_allclose(got[k][ok], np.asarray(want[k])[ok], rtol=tol, atol=1e-12 if exact else 1e-8, err_msg=f"{name} {who}: {k}")
+    assert np.array_equal(got["winner"][ok], rec["winner"][ok])
+    acc, rev = eng.metrics()
+    if ok.all():
+        parity.compare_metrics(acc[0], rev[0], met, rtol=(2e-6 if learnt else 1e-10) if exact else 2e-5, atol=(2e-7 if learnt else 1e-9) if exact else 1e-5,
+                               what=f"{name} metrics-vs-reference")
+    # the winner log: S rows per round, row k = the winner of slot k (agent, item, click), the others invalid
+    if learnt:
+        meta = eng.fit_meta[0, :T * S].cpu().numpy().view(np.uint32).reshape(T, S)
+        valid = (meta >> 31).astype(bool)
+        assert np.array_equal(valid.sum(axis=1)[ok], rec["n_charged"][ok])
+        for t in np.nonzero(ok)[0][:64]:
+            for s in range(P):
+                if rec["won"][t, s]:
+                    k = rec["rank"][t, s]
+                    assert (meta[t, k] >> 12) & 0xFFF == inp["parts"][t, s] and meta[t, k] & 0xFFF == rec["item"][t, s]
+                    assert bool((meta[t, k] >> 30) & 1) == bool(rec["outcome"][t, s])
+    eng.close()
+
+
+def test_multislot_production_rounds_and_fit():
+    """Production mode with max_slots = 3: the slot count is uniform on {1, 2, 3}, revenue grows with it, and the allocator fit
+    consumes the S-rows-per-round winner log (more rows than rounds)."""
+    gu = _gpu()
+    import auction_gym_b200 as ag
+    from auction_gym_b200 import _lib
+
+    case, inp, ref, met = load_golden("rounds_sp_ts")
+    A, I, T = int(case["A"]), int(case["I"]), 6000
+    out = {}
+    for S in (1, 3):
+        eng = ag.Engine(R=2, A=A, I=I, D=int(case["D"]), Do=int(case["Do"]), P=4, mechanism=_lib.SECOND_PRICE, E=case["E"], V=case["V"],
+                        n_items=case["n_items"], alloc_kind=[_lib.ALLOC_TS] * A, bidder_kind=[_lib.BID_TRUTHFUL] * A, precision=_lib.FP32, max_slots=S)
+        eng.set_allocator_state(np.broadcast_to(case["m"], (2,) + case["m"].shape).copy())
+        log = eng.simulate(5, 0, T, ("won", "price"))
+        won = log["won"].cpu().numpy()
+        acc, rev = eng.metrics()
+        info = eng.update_allocators(max_epochs=50).cpu().numpy()
+        out[S] = (won.sum(axis=2), rev, info[..., 3].sum(axis=1))
+        eng.close()
+    n1, rev1, rows1 = out[1]
+    n3, rev3, rows3 = out[3]
+    assert (n1 == 1).all() and (rows1 == T).all()
+    frac = np.bincount(n3.ravel(), minlength=4)[1:] / n3.size
+    assert np.abs(frac - 1 / 3).max() < 0.03                      # rng.integers(1, max_slots + 1), Auction.py:30
+    assert (rows3 == n3.sum(axis=1)).all() and (rows3 > 1.8 * T).all()  # one fit row per charged slot
+    assert (rev3 > 1.5 * rev1).all()

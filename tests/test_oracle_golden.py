@@ -5,7 +5,7 @@ import pytest
 
 from oracle import auction_oracle as ao
 from tests import parity
-from tests.conftest import load_golden, round_golden_names
+from tests.conftest import load_golden, multislot_golden_names, round_golden_names
 
 
 @pytest.mark.parametrize("name", round_golden_names())
@@ -21,6 +21,23 @@ def test_round_loop_matches_reference(name):
                                 est_rtol=parity.RTOL_F32_EST if (learnt or net) else parity.RTOL_F64, what=name, **gtol)
     if rep["near_tie_rounds"] == 0:
         parity.compare_metrics(m["acc"], m["revenue"], met, rtol=2e-6 if (learnt or net) else 1e-10, what=name)
+
+
+@pytest.mark.parametrize("name", multislot_golden_names())
+def test_multislot_rounds_match_reference(name):
+    """Several slots per round (Auction.py:30,60-74 with max_slots 2 / 3 passed to the reference's own instantiate_auction):
+    winners per slot, per-slot clicks, slot-by-slot charging, the log overwritten by the last slot's set_price."""
+    case, inp, ref, met = load_golden(name)
+    assert len(multislot_golden_names()) >= 3 and int(case["max_slots"]) >= 2
+    rec, m = ao.simulate_rounds(case, inp["ctx"], inp["parts"], inp["u"], inp.get("ts_eps"), inp.get("gamma_z"), None, num_slots=inp["num_slots"])
+    for k in ("item", "won", "outcome"):
+        assert np.array_equal(rec[k], ref[k]), k
+    learnt = bool((case["alloc_kind"] != ao.ALLOC_ORACLE).any())
+    tol = parity.RTOL_F32_EST if learnt else parity.RTOL_F64
+    for k in ("bid", "price", "second", "est", "true_ctr", "best_ev", "value"):
+        np.testing.assert_allclose(rec[k], ref[k], rtol=tol, atol=1e-15, err_msg=k)
+    assert (rec["won"].sum(axis=1) == np.minimum(inp["num_slots"], inp["parts"].shape[1] - 1)).all()  # the zip at Auction.py:68
+    parity.compare_metrics(m["acc"], m["revenue"], met, rtol=2e-6 if learnt else 1e-10, atol=2e-7 if learnt else 1e-9, what=name)
 
 
 @pytest.mark.parametrize("name", ["rounds_sp_oracle", "rounds_fp_gauss", "rounds_sp_ts", "rounds_fp_pA", "rounds_sp_p1", "rounds_fp_ties"])
