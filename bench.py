@@ -62,6 +62,8 @@ def parse_args(argv=None):
     ap.add_argument("--no-aux", action="store_true", help="skip the staged-kernel roofline measurements and the shipped config")
     ap.add_argument("--no-full", action="store_true", help="skip the whole-trajectory (100 iterations) measurement")
     ap.add_argument("--full-iterations", type=int, default=WORKLOAD["iterations_full"])
+    ap.add_argument("--subshards", type=int, default=0, help="process this GPU's runs as K independent sub-shards on K CUDA streams "
+                    "(0 = auto: 2 when a GPU holds at most 2048 runs, else 1)")
     return ap.parse_args(argv)
 
 
@@ -83,7 +85,10 @@ def config_dict(args, world, runs_job, scaling, first_it, n_it):
             "agents": w["A"], "items": w["I"], "embedding_size": w["D"], "obs_embedding_size": w["Do"],
             "participants": w["P"], "allocation": "SecondPrice", "allocator": args.allocator, "fit_mode": args.fit_mode,
             "step": "one iteration: T rounds (fused K1-K5) + allocator fits (K6) + metric read-out" + (" + NCCL all-gather of the metric block (K8)" if world > 1 else ""),
-            "parallelism": f"runs sharded over {world} GPU(s) ({scaling} scaling), no data-path collective",
+            "parallelism": f"runs sharded over {world} GPU(s) ({scaling} scaling), no data-path collective" +
+                           (f"; each GPU's runs go as {args.subshards} independent sub-shards on {args.subshards} CUDA streams, so the tail of one "
+                            f"sub-shard's fit grid overlaps the other's kernels (runs are independent, main.py:186-189; results are bit-identical)"
+                            if args.subshards > 1 else ""),
             "l2": "no flush needed: per-step working set (learnt state + winner log + fit workspace, > 400 MB per 512 runs) exceeds the 126 MB L2"}
 
 
@@ -291,74 +296,111 @@ def main():
     K = Do + 1
     learnt = args.allocator == "ts"
     fit_mode = _lib.FIT_ADAM_FAST if args.fit_mode == "adam_fast" else _lib.FIT_ADAM_REF
-    eng = make_engine(ag, _lib, R, T, learnt, local_rank, first_run)
-    if learnt:
-        m0_host = initial_m(first_run, R)
-        m_host = m0_host.clone().pin_memory()
-        q_host = torch.ones((R, A, I, K)).pin_memory()
-        mp_host = m0_host.clone().pin_memory()
-        eng.set_allocator_state(m_host, q_host, mp_host)
-    acc_host = torch.empty((R, A, _lib.NUM_METRICS), dtype=torch.float64).pin_memory()
-    rev_host = torch.empty((R,), dtype=torch.float64).pin_memory()
-    # K8: every iteration's metric block of every rank (main.py:186-222 keeps per-run rows, so gather, not reduce)
-    gathered = torch.empty((world, R, A * _lib.NUM_METRICS + 1), dtype=torch.float64, device=dev) if world > 1 else None
+    if args.subshards <= 0:
+        args.subshards = 2 if (R <= 2048 and R % 2 == 0 and learnt) else 1
+    NS = args.subshards
+    assert R % NS == 0, "--subshards must divide the runs per GPU"
+    Rs = R // NS
+
+    class Sub:  # one sub-shard: its engine, its stream, its pinned host buffers
+        pass
+
+    subs = []
+    for k in range(NS):
+        sb = Sub()
+        sb.first = first_run + k * Rs
+        sb.eng = make_engine(ag, _lib, Rs, T, learnt, local_rank, sb.first)
+        sb.stream = torch.cuda.current_stream(dev) if NS == 1 else torch.cuda.Stream(dev)
+        if learnt:
+            sb.m0_host = initial_m(sb.first, Rs)
+            sb.m_host = sb.m0_host.clone().pin_memory()
+            sb.q_host = torch.ones((Rs, A, I, K)).pin_memory()
+            sb.mp_host = sb.m0_host.clone().pin_memory()
+            sb.eng.set_allocator_state(sb.m_host, sb.q_host, sb.mp_host)
+        sb.acc_host = torch.empty((Rs, A, _lib.NUM_METRICS), dtype=torch.float64).pin_memory()
+        sb.rev_host = torch.empty((Rs,), dtype=torch.float64).pin_memory()
+        # K8: every iteration's metric block of every rank (main.py:186-222 keeps per-run rows, so gather, not reduce)
+        sb.gathered = torch.empty((world, Rs, A * _lib.NUM_METRICS + 1), dtype=torch.float64, device=dev) if world > 1 else None
+        sb.epochs_sum = torch.zeros(2, dtype=torch.float64, device=dev)  # {sum of epochs, fits} over the steps that ask for it
+        subs.append(sb)
+    eng = subs[0].eng
     stream = torch.cuda.current_stream(dev)
+    torch.cuda.synchronize(dev)
     ev_pairs = {"rounds": [], "fit": []}
-    epochs_sum = torch.zeros(2, dtype=torch.float64, device=dev)  # {sum of epochs, fits} over the steps that ask for it
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local_rank])
 
-    def read_out():
+    def read_out(sb):
         """Per-iteration metric read-out: D2H of this rank's block; at N > 1 also the NCCL all-gather (K8)."""
+        e = sb.eng
         if world > 1:
-            blk = torch.cat([eng.acc.reshape(R, -1), eng.revenue.reshape(R, 1)], dim=1)
-            dist.all_gather_into_tensor(gathered.view(world * R, -1), blk)
-        acc_host.copy_(eng.acc, non_blocking=True)
-        rev_host.copy_(eng.revenue, non_blocking=True)
+            blk = torch.cat([e.acc.reshape(Rs, -1), e.revenue.reshape(Rs, 1)], dim=1)
+            dist.all_gather_into_tensor(sb.gathered.view(world * Rs, -1), blk)
+        sb.acc_host.copy_(e.acc, non_blocking=True)
+        sb.rev_host.copy_(e.revenue, non_blocking=True)
 
     def step_device(it, timed, count_epochs=False):
-        """One iteration with everything resident in HBM."""
-        eng.clear_iteration()
-        if timed:
-            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-            e0.record(stream)
-        eng.simulate(SEED, it, T)
-        if timed:
-            e1.record(stream)
-        if learnt:
-            info = eng.update_allocators(want_info=count_epochs, fit_mode=fit_mode)
-            if count_epochs:
-                ran = info[..., 1]
-                epochs_sum.add_(torch.stack([ran.sum(dtype=torch.float64), (ran > 0).sum().to(torch.float64)]))
-        if timed:
-            e2.record(stream)
-            ev_pairs["rounds"].append((e0, e1))
-            ev_pairs["fit"].append((e1, e2))
-        read_out()
+        """One iteration with everything resident in HBM (every sub-shard on its own stream)."""
+        for sb in subs:
+            with torch.cuda.stream(sb.stream):
+                e = sb.eng
+                e.clear_iteration()
+                if timed:
+                    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    e0.record(sb.stream)
+                e.simulate(SEED, it, T)
+                if timed:
+                    e1.record(sb.stream)
+                if learnt:
+                    info = e.update_allocators(want_info=count_epochs, fit_mode=fit_mode)
+                    if count_epochs:
+                        ran = info[..., 1]
+                        sb.epochs_sum.add_(torch.stack([ran.sum(dtype=torch.float64), (ran > 0).sum().to(torch.float64)]))
+                if timed:
+                    e2.record(sb.stream)
+                    ev_pairs["rounds"].append((e0, e1))
+                    ev_pairs["fit"].append((e1, e2))
+                read_out(sb)
 
     def step_e2e(it):
         """The same iteration through the public API with HOST buffers: learnt state up, metrics + state down."""
-        if learnt:
-            eng.set_allocator_state(m_host, q_host, mp_host, non_blocking=True)
-        eng.clear_iteration()
-        eng.simulate(SEED, it, T)
-        if learnt:
-            eng.update_allocators(want_info=False, fit_mode=fit_mode)
-            m_host.copy_(eng.m, non_blocking=True)
-            q_host.copy_(eng.q, non_blocking=True)
-            mp_host.copy_(eng.m_prev, non_blocking=True)
-        read_out()
-        stream.synchronize()
+        for sb in subs:
+            with torch.cuda.stream(sb.stream):
+                e = sb.eng
+                if learnt:
+                    e.set_allocator_state(sb.m_host, sb.q_host, sb.mp_host, non_blocking=True)
+                e.clear_iteration()
+                e.simulate(SEED, it, T)
+                if learnt:
+                    e.update_allocators(want_info=False, fit_mode=fit_mode)
+                    sb.m_host.copy_(e.m, non_blocking=True)
+                    sb.q_host.copy_(e.q, non_blocking=True)
+                    sb.mp_host.copy_(e.m_prev, non_blocking=True)
+                read_out(sb)
+        for sb in subs:  # the step's result is on the host before the next step starts
+            sb.stream.synchronize()
+
+    def join_streams():
+        for sb in subs:
+            if sb.stream is not stream:
+                stream.wait_stream(sb.stream)
+
+    def fork_streams():
+        for sb in subs:
+            if sb.stream is not stream:
+                sb.stream.wait_stream(stream)
 
     def timed_region(fn, steps, it0):
         barrier()
         torch.cuda.synchronize(dev)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(stream)
+        fork_streams()
         for i in range(steps):
             fn(it0 + i)
+        join_streams()
         e.record(stream)
         torch.cuda.synchronize(dev)
         barrier()
@@ -368,26 +410,32 @@ def main():
         return float(ms.item())
 
     def reset_state():
+        torch.cuda.synchronize(dev)
         if learnt:
-            m_host.copy_(m0_host); q_host.fill_(1.0); mp_host.copy_(m0_host)
-            eng.set_allocator_state(m_host, q_host, mp_host)
+            for sb in subs:
+                sb.m_host.copy_(sb.m0_host); sb.q_host.fill_(1.0); sb.mp_host.copy_(sb.m0_host)
+                sb.eng.set_allocator_state(sb.m_host, sb.q_host, sb.mp_host)
+        torch.cuda.synchronize(dev)
 
     # ---- warm-up, then the device-resident timed region: iterations W .. W+K-1 ----
     for it in range(args.warmup):
         step_device(it, False, count_epochs=True)  # same code path as the timed steps (no first-call costs inside the timed region)
     torch.cuda.synchronize(dev)
-    epochs_sum.zero_()
+    for sb in subs:
+        sb.epochs_sum.zero_()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    launches0 = eng.launch_count()
+    launches0 = sum(sb.eng.launch_count() for sb in subs)
     ms_total = timed_region(lambda i: step_device(i, True, count_epochs=True), args.steps, args.warmup)
-    launches = eng.launch_count() - launches0
+    launches = sum(sb.eng.launch_count() for sb in subs) - launches0
     clk = clocks.stop()
     opp_per_step = runs_job * T
     value = opp_per_step * args.steps / (ms_total * 1e-3)
-    k_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) if v else 0.0 for k, v in ev_pairs.items()}
-    per_step_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in ev_pairs.items()}
-    es = epochs_sum.clone()
+    # per-kernel intervals: with sub-shards the intervals of different streams overlap, so the per-step figure is the SUM over the
+    # sub-shards of each one's interval (an upper bound of the kernel's share, exact when NS == 1)
+    per_step_ms = {k: [sum(a.elapsed_time(b) for a, b in v[i * NS:(i + 1) * NS]) for i in range(len(v) // NS)] for k, v in ev_pairs.items()}
+    k_ms = {k: float(np.mean(v)) if v else 0.0 for k, v in per_step_ms.items()}
+    es = torch.stack([sb.epochs_sum for sb in subs]).sum(dim=0)
     if world > 1:
         dist.all_reduce(es)
     fit_epochs_mean = float(es[0] / es[1]) if learnt and float(es[1]) > 0 else None
@@ -413,18 +461,25 @@ def main():
         torch.cuda.synchronize(dev)
         s_all, e_all = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s_all.record(stream)
+        fork_streams()
         for it in range(n_full):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            eng.clear_iteration()
-            eng.simulate(SEED, it, T)
+            a.record(subs[0].stream)
+            acc_ep = []
+            for sb in subs:
+                with torch.cuda.stream(sb.stream):
+                    sb.eng.clear_iteration()
+                    sb.eng.simulate(SEED, it, T)
+                    if learnt:
+                        info = sb.eng.update_allocators(want_info=True, fit_mode=fit_mode)
+                        ran = info[..., 1]
+                        acc_ep.append(torch.stack([ran.sum(dtype=torch.float64), (ran > 0).sum().to(torch.float64)]))
+                    read_out(sb)
             if learnt:
-                info = eng.update_allocators(want_info=True, fit_mode=fit_mode)
-                ran = info[..., 1]
-                info_keep.append(torch.stack([ran.sum(dtype=torch.float64), (ran > 0).sum().to(torch.float64)]))
-            read_out()
-            b.record(stream)
+                info_keep.append(acc_ep)
+            b.record(subs[0].stream)
             per_it.append((a, b))
+        join_streams()
         e_all.record(stream)
         torch.cuda.synchronize(dev)
         barrier()
@@ -434,13 +489,13 @@ def main():
         ms_full = float(ms_full.item())
         ep = None
         if learnt:
-            ep_t = torch.stack(info_keep)
+            ep_t = torch.stack([torch.stack(x).sum(dim=0) for x in info_keep])
             if world > 1:
                 dist.all_reduce(ep_t)
             ep = [float(x[0] / max(float(x[1]), 1.0)) for x in ep_t.cpu()]
         full = {"iterations": n_full, "opportunities": runs_job * T * n_full, "seconds": ms_full * 1e-3,
                 "value": runs_job * T * n_full / (ms_full * 1e-3), "unit": UNIT,
-                "ms_per_iteration": [round(a.elapsed_time(b), 3) for a, b in per_it],
+                "ms_per_iteration": [round(a.elapsed_time(b), 3) for a, b in per_it],  # on sub-shard 0's stream
                 "fit_epochs_mean_per_iteration": [round(x, 1) for x in ep] if ep else None,
                 "target": {"value": 1e9, "n_gpus": 8, "source": "BASELINE.json north_star"},
                 "note": "whole job, max over ranks, device-resident state, per-iteration metric read-out (and all-gather at N > 1) included"}
@@ -452,7 +507,7 @@ def main():
     bytes_fit = R * T * (4 * Do + 4) + R * A * I * K * 4 * 7     # K6: winner records once + m,q,m_prev read, m,q,m_prev,sigma written
     kernels = {}
     if k_ms["rounds"] > 0:
-        kernels["sim_kernel (fused K1-K5)"] = {"ms": k_ms["rounds"], "share": k_ms["rounds"] / (ms_total / args.steps),
+        kernels["sim_kernel (fused K1-K5)"] = {"ms": k_ms["rounds"], "share": k_ms["rounds"] / (k_ms["rounds"] + k_ms["fit"]),
                                                 "algorithmic_bytes": bytes_rounds, "achieved_gbs": bytes_rounds / k_ms["rounds"] / 1e6,
                                                 "opportunities_per_s": R * T / k_ms["rounds"] * 1e3,
                                                 # production mode draws the Thompson noise in logit space: one normal per (participant, item)
@@ -462,17 +517,21 @@ def main():
                                                 "from_profile": profile_numbers(r"sim_kernel", None)}
     if learnt and k_ms["fit"] > 0:
         fit_epochs_total = float(es[0]) / max(world, 1)
-        kernels["fit kernels (K6)"] = {"ms": k_ms["fit"], "share": k_ms["fit"] / (ms_total / args.steps), "ms_per_step": per_step_ms["fit"],
+        kernels["fit kernels (K6)"] = {"ms": k_ms["fit"], "share": k_ms["fit"] / (k_ms["rounds"] + k_ms["fit"]), "ms_per_step": per_step_ms["fit"],
                                        "algorithmic_bytes": bytes_fit, "achieved_gbs": bytes_fit / k_ms["fit"] / 1e6,
                                        "fits_per_s": R * A / k_ms["fit"] * 1e3, "rows_per_fit": rows_per_fit,
                                        "fit_epochs_per_s": fit_epochs_total / (k_ms["fit"] * args.steps) * 1e3,
                                        "bound": "instruction issue: thousands of sequential Adam epochs per fit on register / shared-memory resident state",
-                                       "from_profile": profile_numbers(r"fit_warp_kernel<3", R * A)}
+                                       "from_profile": profile_numbers(r"fit_warp_kernel<3", Rs * A),
+                                       "subshards": NS}
+    for v in kernels.values():
+        v["ms_note"] = ("CUDA events on the launching stream around the kernel(s), mean over the timed steps" +
+                        ("; summed over the sub-shards, whose streams overlap (share = of the two sums)" if NS > 1 else ""))
     aux = {}
     if not args.no_aux:
         # staged resolution kernel K4(+K5) on this GPU's resident runs: HBM-bound.  With the per-agent accumulation it moves
         # 13P + 10 = 36 B/opportunity; resolution + click alone never reads the values and agent ids: 8P + 10 = 26 B
-        Rk = R
+        Rk = Rs
         engk = eng
         engk.clear_iteration()
         b = engk.staged_round(SEED, 0, T)
@@ -552,12 +611,14 @@ def main():
                         "note": "same iterations of the same trajectory as `value` (restart from the initial host state, same warm-up); every step "
                                 "uploads the learnt state from pinned host memory and reads state + metrics back"},
                 "gpu_launches": int(launches), "gpu_launches_note": "agym_launch_count difference over the timed region on rank 0 (sim_kernel, bucket_kernel, "
-                                                                     "fit_classify_kernel, fit_order_kernel, two fit_warp_kernel instantiations per step)",
+                                                                     "fit_classify_kernel, fit_order_kernel, two fit_warp_kernel instantiations per step and sub-shard)",
+                "subshards": NS,
                 "round_loop": {"value": runs_job * T / k_ms["rounds"] * 1e3 if k_ms["rounds"] else None, "unit": UNIT, "ms": k_ms["rounds"]},
                 "full_workload": full,
                 "roofline": roofline, "roofline_kernels": {**kernels, **aux}, "cpu_baseline": cpu, "shipped_config": shipped, "clocks": clk}
         print(json.dumps(line), flush=True)
-    eng.close()
+    for sb in subs:
+        sb.eng.close()
     if world > 1:
         dist.destroy_process_group()
 
