@@ -134,6 +134,7 @@ int agym_destroy(agym_handle* h) {
   cudaFree(h->d_n_items); cudaFree(h->d_alloc_kind); cudaFree(h->d_bidder_kind); cudaFree(h->d_bidder_fit);
   cudaFree(h->d_E64); cudaFree(h->d_V64); cudaFree(h->d_E32); cudaFree(h->d_V32);
   cudaFree(h->d_memory); cudaFree(h->d_mem_off);
+  destroy_comm(h);
   cudaFree(h->d_fit_epochs); cudaFree(h->est_scratch);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);

@@ -234,6 +234,8 @@ struct agym_handle {
   int num_sms = 148;
   unsigned long long launches = 0;  // kernels of this library launched through this handle (agym_launch_count)
   // second stream for kernels that run beside each other inside one call (fork / join with events; created on first use)
+  void* nccl_comm = nullptr;     // ncclComm_t of agym_comm_init (agym_nccl.cu), one per handle
+  int nccl_rank = 0, nccl_world = 1;
   int* d_fit_epochs = nullptr;   // [R*A] epochs of each allocator fit in the previous update (launch-order hint, owned)
   size_t fit_epochs_len = 0;
   cudaStream_t aux_stream = nullptr;
@@ -247,6 +249,7 @@ struct agym_handle {
 
 namespace agym {
 int set_error(agym_handle* h, int code, const std::string& msg);
+void destroy_comm(agym_handle* h);
 int check_cuda(agym_handle* h, cudaError_t e, const char* what);
 SimParams make_params(const agym_handle* h);
 

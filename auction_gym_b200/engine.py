@@ -405,6 +405,39 @@ class Engine:
                                           _ptr(bid), _ptr(gamma), _ptr(prop), self._stream()))
         return float(bid[run, 0]), float(gamma[run, 0]), float(prop[run, 0])
 
+    # ------------------------------------------------------------------ K8: the metric gather (NCCL through the C ABI)
+    def comm_init(self, rank=None, world=None):
+        """Create this engine's NCCL communicator (include/agym.h: agym_comm_init).  Under torch.distributed the unique id is
+        broadcast from rank 0; with world == 1 no process group is needed."""
+        import ctypes
+
+        if world is None:
+            import torch.distributed as dist
+
+            rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            rc = self.lib.agym_nccl_unique_id(buf)
+            if rc != 0:
+                raise AgymError(f"agym_nccl_unique_id failed ({rc}): {self.lib.agym_last_error(None).decode()}")
+        ident = [buf.raw]
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.broadcast_object_list(ident, src=0)
+        self._check(self.lib.agym_comm_init(self.handle, ident[0], int(rank), int(world)))
+        self.comm_world = int(world)
+        self.gathered_acc = torch.empty((self.comm_world, self.R, self.A, _lib.NUM_METRICS), dtype=torch.float64, device=self.device)
+        self.gathered_revenue = torch.empty((self.comm_world, self.R), dtype=torch.float64, device=self.device)
+
+    def gather_metrics(self):
+        """All-gather of every rank's accumulator block and revenue (agym_gather_metrics_nccl) on the current stream:
+        returns device tensors [world, R, A, NUM_METRICS] and [world, R]."""
+        if not getattr(self, "comm_world", 0):
+            raise AgymError("gather_metrics: call comm_init first")
+        self._check(self.lib.agym_gather_metrics_nccl(self.handle, _ptr(self.gathered_acc), _ptr(self.gathered_revenue), self._stream()))
+        return self.gathered_acc, self.gathered_revenue
+
     # ------------------------------------------------------------------ results
     def metrics(self):
         """(acc [R, A, NUM_METRICS], revenue [R]) as numpy arrays (one D2H copy each)."""

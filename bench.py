@@ -320,7 +320,8 @@ def main():
         sb.acc_host = torch.empty((Rs, A, _lib.NUM_METRICS), dtype=torch.float64).pin_memory()
         sb.rev_host = torch.empty((Rs,), dtype=torch.float64).pin_memory()
         # K8: every iteration's metric block of every rank (main.py:186-222 keeps per-run rows, so gather, not reduce)
-        sb.gathered = torch.empty((world, Rs, A * _lib.NUM_METRICS + 1), dtype=torch.float64, device=dev) if world > 1 else None
+        if world > 1:
+            sb.eng.comm_init(rank, world)  # this sub-shard's NCCL communicator (agym_comm_init; the id is broadcast by torch.distributed)
         sb.epochs_sum = torch.zeros(2, dtype=torch.float64, device=dev)  # {sum of epochs, fits} over the steps that ask for it
         subs.append(sb)
     eng = subs[0].eng
@@ -336,8 +337,7 @@ def main():
         """Per-iteration metric read-out: D2H of this rank's block; at N > 1 also the NCCL all-gather (K8)."""
         e = sb.eng
         if world > 1:
-            blk = torch.cat([e.acc.reshape(Rs, -1), e.revenue.reshape(Rs, 1)], dim=1)
-            dist.all_gather_into_tensor(sb.gathered.view(world * Rs, -1), blk)
+            e.gather_metrics()  # agym_gather_metrics_nccl: ncclAllGather of the [Rs, A, 12] block and the revenue on this stream
         sb.acc_host.copy_(e.acc, non_blocking=True)
         sb.rev_host.copy_(e.revenue, non_blocking=True)
 

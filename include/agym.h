@@ -202,6 +202,17 @@ int agym_retain_logs(agym_handle* h, void* stream);
 int agym_estimate_ctr(agym_handle* h, int32_t run, int32_t agent, const double* context, int32_t sample, const float* eps, uint64_t seed,
                       int32_t iter, int64_t query, double* out, void* stream);
 
+/* ---- K8: the job's one collective (src/main.py:186-222 keeps a row per run, agent and iteration, so gather, not reduce) ----
+ * NCCL is bound at run time (dlopen of libnccl.so.2); a single-GPU caller never needs it.
+ * agym_nccl_unique_id: rank 0 fills 128 bytes (ncclUniqueId) and ships them to the other ranks by its own means.
+ * agym_comm_init: every rank, same id; creates this handle's communicator on its device (collective call).
+ * agym_gather_metrics_nccl: all-gather of the bound accumulators [R][A][AGYM_NUM_METRICS] and revenue [R] into
+ *   recv_acc [world][R][A][AGYM_NUM_METRICS] and recv_revenue [world][R] (device pointers) on `stream`; every rank holds
+ *   the same R (pad the last shard). */
+int agym_nccl_unique_id(char* out128);
+int agym_comm_init(agym_handle* h, const char* id128, int32_t rank, int32_t world);
+int agym_gather_metrics_nccl(agym_handle* h, double* recv_acc, double* recv_revenue, void* stream);
+
 /* Number of kernels of this library launched through this handle so far (bench.py's gpu_launches is a difference of
  * two readings; the reference has no counterpart: it launches nothing). */
 uint64_t agym_launch_count(const agym_handle* h);

@@ -308,3 +308,22 @@ def test_resume_from_checkpoint_equals_the_uninterrupted_job(tmp_path, cfg, over
     rest = driver.run_experiment(path, checkpoint_dir=ck, resume=True)
     np.testing.assert_array_equal(rest["metrics"], whole["metrics"])
     np.testing.assert_array_equal(rest["revenue"], whole["revenue"])
+
+
+def test_metric_gather_through_the_abi_single_rank():
+    """K8 through the C ABI (agym_nccl_unique_id / agym_comm_init / agym_gather_metrics_nccl) with a one-rank communicator:
+    the gathered block is this rank's block.  (Two and more ranks: bench.py under torchrun, profiles/r2_bench_n2_line.json.)"""
+    _need_gpu()
+    import torch
+    from tests.conftest import load_golden
+    from tests import gpu_util as gu
+    from auction_gym_b200 import _lib
+
+    case, *_ = load_golden("rounds_sp_oracle")
+    eng = gu.engine_from_case(case, R=3, precision=_lib.FP32)
+    eng.simulate(1, 0, 500)
+    eng.comm_init(0, 1)
+    acc_g, rev_g = eng.gather_metrics()
+    torch.cuda.synchronize()
+    assert acc_g.shape == (1, 3, eng.A, _lib.NUM_METRICS) and torch.equal(acc_g[0], eng.acc) and torch.equal(rev_g[0], eng.revenue)
+    eng.close()
