@@ -15,7 +15,7 @@ BIDDER_D = 4
 BIDDER_W = 16
 BID_ROW = 5
 TERM_ROW = 8         # AGYM_TERM_ROW
-FIT_ADAM_REF, FIT_ADAM_FAST = 0, 1
+FIT_ADAM_REF, FIT_ADAM_FAST, FIT_NEWTON = 0, 1, 2  # FIT_NEWTON: opt-in, a different algorithm (include/agym.h)
 (BFIT_NONE, BFIT_VL_SEARCH, BFIT_VL_POLICY, BFIT_PL_REINFORCE, BFIT_PL_OFFPOLICY, BFIT_PL_TRPO, BFIT_PL_PPO, BFIT_DR, BFIT_EMPIRICAL) = range(9)
 ABI_VERSION = 2
 

@@ -47,6 +47,7 @@ class Auction:
         # run driven from Python): the allocator's constructor draw, from the rng the caller passed, as Models.py:21-24 does.
         self.per_run_init = bool(self.num_runs > 1 or self.run_offset) if per_run_init is None else bool(per_run_init)
         self.iteration = 0
+        self.fit_mode = _lib.FIT_ADAM_REF  # allocator fit arithmetic (include/agym.h: agym_fit_mode); FIT_NEWTON is opt-in, a different algorithm
         self.engine = None
         self._rounds_capacity = int(rounds_capacity)
         self._models_updated = False
@@ -149,7 +150,7 @@ class Auction:
         if unsupported:
             raise _lib.AgymError(f"bidder update for {unsupported} (K7, src/Bidder.py:60-147,278-316,369-431,477-615) is not built yet; "
                                  "see DESIGN.md 'not yet built'")
-        self.engine.update_allocators(want_info=False)
+        self.engine.update_allocators(want_info=False, fit_mode=self.fit_mode)
         info = self.engine.update_bidders(self.seed, self.iteration)
         if info is not None and bool((info[..., 1] > 0).logical_and(info[..., 2].isnan()).any()):
             raise _lib.AgymError("NaN loss in a bidder fit (the reference prints 'NAN DETECTED!' and exits, Bidder.py:412-419,598-605)")

@@ -406,7 +406,7 @@ int agym_set_option(agym_handle* h, const char* name, double value) {
 
 int agym_update_allocators(agym_handle* h, int32_t fit_mode, int32_t max_epochs, float* fit_info, void* stream) {
   if (!h) return AGYM_ERR_INVALID;
-  if (fit_mode != AGYM_FIT_ADAM_REF && fit_mode != AGYM_FIT_ADAM_FAST) return set_error(h, AGYM_ERR_INVALID, "agym_update_allocators: unknown fit mode");
+  if (fit_mode != AGYM_FIT_ADAM_REF && fit_mode != AGYM_FIT_ADAM_FAST && fit_mode != AGYM_FIT_NEWTON) return set_error(h, AGYM_ERR_INVALID, "agym_update_allocators: unknown fit mode");
   if (!h->any_learnt) return AGYM_OK;
   if (!h->m || !h->q || !h->m_prev || !h->sigma) return set_error(h, AGYM_ERR_STATE, "agym_update_allocators: allocator state not bound");
   if (!h->fit_ctx) return set_error(h, AGYM_ERR_STATE, "agym_update_allocators: fit log not bound");

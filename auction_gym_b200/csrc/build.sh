@@ -8,7 +8,7 @@ OUT="$HERE/../libagym.so"
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -cudart static -I$ROOT/include -I$HERE"
 mkdir -p "$HERE/obj"
 pids=()
-SRCS="agym_api agym_sim agym_staged agym_fit agym_fit_warp agym_bidfit agym_retain agym_nccl"
+SRCS="agym_api agym_sim agym_staged agym_fit agym_fit_warp agym_fit_newton agym_bidfit agym_retain agym_nccl"
 OBJS=""
 for f in $SRCS; do
   OBJS="$OBJS $HERE/obj/$f.o"

@@ -182,7 +182,11 @@ def gather_runs(local, world):
     return np.concatenate([p[:int(c.item())].cpu().numpy() for p, c in zip(parts, counts)], axis=0)
 
 
-def run_experiment(config_path, device=0, rank=0, world=1, precision=None, verbose=False, checkpoint_dir=None, resume=False, stop_after=None):
+FIT_MODES = {"adam_ref": _lib.FIT_ADAM_REF, "adam_fast": _lib.FIT_ADAM_FAST, "newton": _lib.FIT_NEWTON}
+
+
+def run_experiment(config_path, device=0, rank=0, world=1, precision=None, verbose=False, checkpoint_dir=None, resume=False, stop_after=None,
+                   fit_mode="adam_ref"):
     """Parse the config, simulate this rank's share of the runs, gather.  Returns a dict with the reference's
     run -> agent -> per-iteration structure flattened into arrays (see ``write_csvs``)."""
     rng, config, agent_configs, agents2items, agents2item_values, num_runs, max_slots, embedding_size, embedding_var, \
@@ -196,6 +200,7 @@ def run_experiment(config_path, device=0, rank=0, world=1, precision=None, verbo
             rng, config, agents2items, agents2item_values, agents, max_slots, embedding_size, embedding_var, obs_embedding_size,
             num_runs=count, run_offset=first, device=device, precision=precision, seed=config["random_seed"],
             rounds_capacity=config["rounds_per_iter"], per_run_init=True)
+        auction.fit_mode = FIT_MODES[fit_mode]  # "newton": opt-in, NOT the reference's algorithm (csrc/agym_fit_newton.cu)
         ckpt = None
         if checkpoint_dir:
             os.makedirs(checkpoint_dir, exist_ok=True)
@@ -266,6 +271,8 @@ def main(argv=None):
     parser.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     parser.add_argument("--checkpoint-dir", default=None, help="write the learnt state after every iteration (one file per rank)")
     parser.add_argument("--resume", action="store_true", help="continue from --checkpoint-dir")
+    parser.add_argument("--fit-mode", default="adam_ref", choices=sorted(FIT_MODES),
+                        help="allocator fit: adam_ref = the reference's Adam trajectory (default); newton = opt-in regularised Newton solve, a different algorithm")
     args = parser.parse_args(argv)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
@@ -276,7 +283,7 @@ def main(argv=None):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     result = run_experiment(args.config, device=local, rank=rank, world=world,
                             precision=_lib.FP64 if args.precision == "fp64" else _lib.FP32, verbose=True,
-                            checkpoint_dir=args.checkpoint_dir, resume=args.resume)
+                            checkpoint_dir=args.checkpoint_dir, resume=args.resume, fit_mode=args.fit_mode)
     if rank == 0:
         out = write_csvs(result, args.output_dir)
         print(f"wrote CSVs to {out}")

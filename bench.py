@@ -57,7 +57,8 @@ def parse_args(argv=None):
     ap.add_argument("--runs-per-gpu", type=int, default=0, help="weak scaling: runs per GPU (overrides --runs-total)")
     ap.add_argument("--rounds", type=int, default=WORKLOAD["T"])
     ap.add_argument("--allocator", default="ts", choices=["ts", "oracle"], help="ts = SP_Truthful_TS shape (headline); oracle = SP_Oracle shape")
-    ap.add_argument("--fit-mode", default="adam_ref", choices=["adam_ref", "adam_fast"])
+    ap.add_argument("--fit-mode", default="adam_ref", choices=["adam_ref", "adam_fast", "newton"],
+                    help="adam_ref: the reference's algorithm (the headline); newton: opt-in, a different algorithm, never comparable with the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the staged-kernel roofline measurements and the shipped config")
     ap.add_argument("--no-full", action="store_true", help="skip the whole-trajectory (100 iterations) measurement")
@@ -237,14 +238,17 @@ def run_reference_arm(args, rank, world):
                                                fits_per_worker=fits_per_worker, workers=workers, learnt=learnt, seed=i, pool=pool))
 
     def agg(rs):
+        # whole-job throughput, as the GPU arm's `value`: K steps' opportunities / the time K steps take on `workers` cores
+        # (NOT the mean of per-step rates, which would weight the cheap late iterations like the expensive early ones)
         if learnt:
-            return float(np.mean([r["aggregate_opp_per_s"] for r in rs]))
-        return float(np.mean([r["round_only_per_core"] for r in rs])) * workers
+            secs = [args.rounds / r["round_only_per_core"] + w["A"] * r["fit_seconds_mean"] for r in rs]  # one run's iteration on one core
+            return workers * args.rounds * len(rs) / float(np.sum(secs))
+        return workers * len(rs) / float(np.sum([1.0 / r["round_only_per_core"] for r in rs]))
 
     value = agg(rows)
     sample = (f"per step i (iteration {args.warmup} + i of the GPU arm's trajectory) and per core: {n_rounds} rounds of the {'unmodified reference' if kind == 'reference' else 'numpy port'}'s "
               f"simulate_opportunity at the bench shape + {fits_per_worker} allocator fit(s) on the dumped inputs of that iteration "
-              f"(tests/golden/bench_fit_inputs.npz); {workers} processes, one torch thread each; opportunities/s = T / (T / round_rate + A * fit_seconds) summed over cores")
+              f"(tests/golden/bench_fit_inputs.npz); {workers} processes, one torch thread each; opportunities/s = cores * K * T / sum over the K steps of (T / round_rate + A * fit_seconds)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean([r["wall_seconds"] for r in rows])), "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32/f64 (the reference's own mix)", "data": "synthetic",
@@ -295,7 +299,7 @@ def main():
     first_run, R, runs_job, scaling = shard(args, world, rank)
     K = Do + 1
     learnt = args.allocator == "ts"
-    fit_mode = _lib.FIT_ADAM_FAST if args.fit_mode == "adam_fast" else _lib.FIT_ADAM_REF
+    fit_mode = {"adam_ref": _lib.FIT_ADAM_REF, "adam_fast": _lib.FIT_ADAM_FAST, "newton": _lib.FIT_NEWTON}[args.fit_mode]
     if args.subshards <= 0:
         args.subshards = 2 if (R <= 2048 and R % 2 == 0 and learnt) else 1
     NS = args.subshards
@@ -451,10 +455,9 @@ def main():
     d2h = state_bytes + R * A * _lib.NUM_METRICS * 8 + R * 8
 
     # ---- the whole trajectory: N = 100 iterations from the initial state ----
-    full = None
-    if not args.no_full:
+    def trajectory(n_full, mode):
+        """n_full iterations from the initial state with allocator fit mode `mode`, timed as one region (max over ranks)."""
         reset_state()
-        n_full = args.full_iterations
         per_it = []
         info_keep = []
         barrier()
@@ -471,7 +474,7 @@ def main():
                     sb.eng.clear_iteration()
                     sb.eng.simulate(SEED, it, T)
                     if learnt:
-                        info = sb.eng.update_allocators(want_info=True, fit_mode=fit_mode)
+                        info = sb.eng.update_allocators(want_info=True, fit_mode=mode)
                         ran = info[..., 1]
                         acc_ep.append(torch.stack([ran.sum(dtype=torch.float64), (ran > 0).sum().to(torch.float64)]))
                     read_out(sb)
@@ -493,12 +496,25 @@ def main():
             if world > 1:
                 dist.all_reduce(ep_t)
             ep = [float(x[0] / max(float(x[1]), 1.0)) for x in ep_t.cpu()]
-        full = {"iterations": n_full, "opportunities": runs_job * T * n_full, "seconds": ms_full * 1e-3,
+        welfare = float(sum(float(sb.acc_host[..., _lib.M_GROSS].sum()) for sb in subs) / R)  # last iteration, mean over this rank's runs
+        return {"iterations": n_full, "opportunities": runs_job * T * n_full, "seconds": ms_full * 1e-3,
                 "value": runs_job * T * n_full / (ms_full * 1e-3), "unit": UNIT,
                 "ms_per_iteration": [round(a.elapsed_time(b), 3) for a, b in per_it],  # on sub-shard 0's stream
                 "fit_epochs_mean_per_iteration": [round(x, 1) for x in ep] if ep else None,
-                "target": {"value": 1e9, "n_gpus": 8, "source": "BASELINE.json north_star"},
-                "note": "whole job, max over ranks, device-resident state, per-iteration metric read-out (and all-gather at N > 1) included"}
+                "welfare_last_iteration_per_run": welfare}
+
+    # ---- the whole trajectory: N = 100 iterations from the initial state ----
+    full, newton = None, None
+    if not args.no_full:
+        full = trajectory(args.full_iterations, fit_mode)
+        full.update(target={"value": 1e9, "n_gpus": 8, "source": "BASELINE.json north_star"},
+                    note="whole job, max over ranks, device-resident state, per-iteration metric read-out (and all-gather at N > 1) included")
+        if learnt and fit_mode != _lib.FIT_NEWTON:
+            newton = trajectory(args.full_iterations, _lib.FIT_NEWTON)
+            newton.update(fit_mode="newton", fit_passes_mean_per_iteration=newton.pop("fit_epochs_mean_per_iteration"),
+                          note="OPT-IN mode AGYM_FIT_NEWTON, a DIFFERENT ALGORITHM from the reference's (regularised Newton solve per item instead "
+                               "of the Adam trajectory; csrc/agym_fit_newton.cu): its own learning trajectory, no parity claim, not comparable "
+                               "with `value`, `e2e` or the reference arm; reported because BASELINE.json's north star names Newton / Laplace fits")
 
     # ---- roofline bookkeeping ----
     peak, peak_src = measured_peaks()
@@ -614,7 +630,7 @@ def main():
                                                                      "fit_classify_kernel, fit_order_kernel, two fit_warp_kernel instantiations per step and sub-shard)",
                 "subshards": NS,
                 "round_loop": {"value": runs_job * T / k_ms["rounds"] * 1e3 if k_ms["rounds"] else None, "unit": UNIT, "ms": k_ms["rounds"]},
-                "full_workload": full,
+                "full_workload": full, "opt_in_newton_mode": newton,
                 "roofline": roofline, "roofline_kernels": {**kernels, **aux}, "cpu_baseline": cpu, "shipped_config": shipped, "clocks": clk}
         print(json.dumps(line), flush=True)
     for sb in subs:

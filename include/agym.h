@@ -227,7 +227,12 @@ int agym_set_option(agym_handle* h, const char* name, double value);
 /* ---- per-iteration model updates ---- */
 enum agym_fit_mode {
   AGYM_FIT_ADAM_REF = 0,  /* IEEE divide / sqrt, accurate expf / logf: the operations torch's CPU kernels perform */
-  AGYM_FIT_ADAM_FAST = 1  /* same state machine with MUFU approximations (~2 ulp); sparse regime only, else == REF */
+  AGYM_FIT_ADAM_FAST = 1, /* same state machine with MUFU approximations (~2 ulp); sparse regime only, else == REF */
+  AGYM_FIT_NEWTON = 2     /* OPT-IN, a different algorithm: damped Newton per item to the optimum of the reference's objective
+                           * (Models.py:39-41) instead of the reference's Adam trajectory, which stops short of it; the Laplace
+                           * update and update_prior (Models.py:43-48) are the reference's.  obs_embedding_size 4 only.  Never a
+                           * parity claim: max_epochs = objective evaluations per item (0 = 50); fit_info = {max passes over
+                           * the items, total passes, objective, rows}. */
 };
 /* PyTorchLogisticRegressionAllocator.update for every (run, learnt agent) on the winner records of
  * this iteration (BidderAllocation.py:29-65, Models.py:35-48).  fit_info (device, nullable)

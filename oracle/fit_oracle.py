@@ -111,6 +111,74 @@ def fit_allocator(X, items, y, m0, q0, m_prev, max_epochs=MAX_EPOCHS, return_los
     return out
 
 
+def allocator_objective(X, items, y, m, q, m_prev, prior_on_intercept=False):
+    """The reference's training objective (Models.py:39-41) in float64: BCE sum + 0.5 * sum over the context columns of
+    q (prev_iter_m - m)^2 (``prior_on_intercept``: over all columns, AGYM_FIT_NEWTON's objective), and its gradient."""
+    X, y = np.asarray(X, np.float64), np.asarray(y, np.float64)
+    m, q, m_prev = (np.asarray(a, np.float64) for a in (m, q, m_prev))
+    z = (X * m[items]).sum(axis=1)
+    nll = np.logaddexp(0.0, -z) * y + np.logaddexp(0.0, z) * (1 - y)
+    qq = q.copy()
+    if not prior_on_intercept:
+        qq[:, -1] = 0.0
+    d = m - m_prev
+    grad = np.zeros_like(m)
+    np.add.at(grad, items, (1 / (1 + np.exp(-z)) - y)[:, None] * X)
+    grad += qq * d
+    return float(nll.sum() + 0.5 * (qq * d * d).sum()), grad
+
+
+def fit_allocator_newton(X, items, y, m0, q0, m_prev, max_passes=50):
+    """Restatement (float64) of the OPT-IN fit mode AGYM_FIT_NEWTON (csrc/agym_fit_newton.cu) -- NOT a reference algorithm.
+
+    Per item with rows: damped Newton on the reference's likelihood with the Gaussian prior N(m_prev, 1/q) on ALL columns (the
+    reference's loss, Models.py:39-41, leaves the intercept out, which puts the optimum of an all-click / no-click item at
+    infinity), step halving when the objective does not decrease, stop when the Newton decrement g . d < 1e-9; then the
+    reference's Laplace update with its literal exp(1 - z) (Models.py:43-45).  Returns dict(m, q, passes [I])."""
+    X = np.asarray(X, np.float64)
+    items = np.asarray(items, np.int64)
+    y = np.asarray(y, np.float64)
+    m = np.array(m0, np.float64, copy=True)
+    q = np.array(q0, np.float64, copy=True)
+    m_prev = np.asarray(m_prev, np.float64)
+    I, K = m.shape
+    passes = np.zeros(I, np.int64)
+    if len(y) < 2:  # BidderAllocation.py:33
+        return {"m": m.astype(f32), "q": q.astype(f32), "passes": passes}
+    for it in range(I):
+        sel = items == it
+        if not sel.any():
+            continue
+        Xi, yi = X[sel], y[sel]
+        qi = q[it].copy()
+        acc, loss_acc, delta, alpha, trial = m[it].copy(), np.inf, np.zeros(K), 1.0, m[it].copy()
+        while True:
+            z = Xi @ trial
+            e = np.exp(-np.abs(z))
+            p1 = np.where(z >= 0, 1 / (1 + e), e / (1 + e))
+            w = e / (1 + e) ** 2
+            d = trial - m_prev[it]
+            loss = (np.log1p(e) + np.where((yi > 0.5) == (z >= 0), 0.0, np.abs(z))).sum() + 0.5 * (qi * d * d).sum()
+            g = Xi.T @ (p1 - yi) + qi * d
+            H = (Xi * w[:, None]).T @ Xi + np.diag(qi)
+            passes[it] += 1
+            if not loss <= loss_acc + 1e-6 * (1.0 + abs(loss_acc)):
+                alpha *= 0.5
+                if alpha < 1.0 / 1024 or passes[it] >= max_passes:
+                    break
+                trial = acc - alpha * delta
+                continue
+            acc, loss_acc = trial, loss
+            delta = np.linalg.solve(H * (1 + 1e-12 * np.eye(K)) + 1e-12 * np.eye(K), g)
+            if g @ delta < 1e-9 or passes[it] >= max_passes:
+                break
+            alpha, trial = 1.0, acc - delta
+        m[it] = acc
+        P = 1.0 / (1.0 + np.exp(1.0 - Xi @ acc))
+        q[it] += ((P * (1 - P))[:, None] * Xi * Xi).sum(axis=0)
+    return {"m": m.astype(f32), "q": q.astype(f32), "passes": passes}
+
+
 # ----------------------------------------------------------------------------------------------
 # ValueLearningBidder / DoublyRobustBidder win-rate model  (Bidder.py:218-260, 501-538; Models.py:51-62)
 # ----------------------------------------------------------------------------------------------

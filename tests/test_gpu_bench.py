@@ -36,6 +36,9 @@ def test_bench_line_carries_the_contract_keys():
     f = d["full_workload"]
     assert f["iterations"] == 4 and len(f["ms_per_iteration"]) == 4 and len(f["fit_epochs_mean_per_iteration"]) == 4
     assert abs(f["value"] - 16 * 2000 * 4 / f["seconds"]) <= 1e-6 * f["value"]
+    nw = d["opt_in_newton_mode"]  # reported strictly apart from the headline: a different algorithm
+    assert nw["fit_mode"] == "newton" and "DIFFERENT ALGORITHM" in nw["note"] and nw["iterations"] == 4
+    assert all(1 <= x <= 50 * 64 for x in nw["fit_passes_mean_per_iteration"]) and nw["welfare_last_iteration_per_run"] > 0
     r = d["roofline"]
     assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     k4 = d["roofline_kernels"]["k4_resolve"]

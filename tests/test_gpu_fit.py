@@ -232,3 +232,56 @@ def test_every_fit_kernel_matches_the_oracle_on_a_fixed_budget(name, variant):
         np.testing.assert_allclose(info[j, 2], orc["final_loss"], rtol=2e-5, err_msg=what)
         np.testing.assert_array_equal(mp[j], m1[j])
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["fit_ref_shape", "fit_64x64"])
+@pytest.mark.parametrize("it", [0, 1])
+def test_newton_mode_solves_its_stated_objective(name, it):
+    """AGYM_FIT_NEWTON is opt-in and NOT the reference's algorithm (csrc/agym_fit_newton.cu): there is no trajectory to compare.
+    What can be checked: on the reference-run fit inputs it reaches the optimum of its stated objective (the reference's
+    likelihood + the Gaussian prior on every column) -- gradient ~ 0, objective below the reference's own end point -- it agrees
+    with the float64 restatement, and the bookkeeping around the solve (Laplace update, update_prior, untouched items,
+    sigma) is the reference's."""
+    import torch
+
+    from auction_gym_b200 import _lib
+
+    gu = _gpu()
+    z = np.load(f"{GOLDEN_DIR}/{name}.npz")
+    agents = [int(a) for a in z["fit_agents"]]
+    pre = [f"it{it}_a{a}_" for a in agents]
+    I, K = z[pre[0] + "m0"].shape
+    Do = K - 1
+    rows = []
+    for j, p in enumerate(pre):
+        X, items, y = z[p + "X"], z[p + "items"], z[p + "y"]
+        rows += [(r, j, X[r, :Do], items[r], y[r]) for r in range(len(y))]
+    rows.sort(key=lambda t: (t[0], t[1]))
+    T = len(rows)
+    eng = _engine_for_fits(gu, len(agents), I, Do, T)
+    eng.fit_ctx[0, :T].copy_(torch.from_numpy(np.stack([r[2] for r in rows]).astype(np.float32)))
+    meta = _pack_meta(np.array([r[1] for r in rows]), np.array([r[3] for r in rows]), np.array([r[4] for r in rows]) > 0)
+    eng.fit_meta[0, :T].copy_(torch.from_numpy(meta.view(np.int32)))
+    eng._check(eng.lib.agym_set_rounds_in_iteration(eng.handle, T))
+    eng.set_allocator_state(np.stack([z[p + "m0"] for p in pre])[None], np.stack([z[p + "q0"] for p in pre])[None],
+                            np.stack([z[p + "m_prev"] for p in pre])[None])
+    info = eng.update_allocators(fit_mode=_lib.FIT_NEWTON).cpu().numpy()[0]
+    m1, q1, mp, sg = (t.cpu().numpy()[0] for t in (eng.m, eng.q, eng.m_prev, eng.sigma))
+    for j, p in enumerate(pre):
+        X, items, y = z[p + "X"], z[p + "items"], z[p + "y"]
+        what = f"{name} it{it} agent {agents[j]} (rows {len(y)}, passes {info[j, 0]:.0f} max / {info[j, 1]:.0f} total)"
+        assert info[j, 3] == len(y) and 1 <= info[j, 0] <= 50, what
+        obj, grad = fo.allocator_objective(X, items, y, m1[j], z[p + "q0"], z[p + "m_prev"], prior_on_intercept=True)
+        obj_ref, _ = fo.allocator_objective(X, items, y, z[p + "m1"], z[p + "q0"], z[p + "m_prev"], prior_on_intercept=True)
+        assert np.abs(grad).max() < 2e-3, what      # float32 row arithmetic: the float64 restatement stops at ~1e-4
+        assert obj <= obj_ref + 1e-6, what          # never worse than where the reference's Adam trajectory stopped
+        np.testing.assert_allclose(info[j, 2], obj, rtol=1e-5, err_msg=what)
+        orc = fo.fit_allocator_newton(X, items, y, z[p + "m0"], z[p + "q0"], z[p + "m_prev"])
+        np.testing.assert_allclose(m1[j], orc["m"], atol=2e-4, err_msg=what)
+        np.testing.assert_allclose(q1[j], orc["q"], rtol=2e-4, err_msg=what)
+        used = np.unique(items)
+        unused = np.setdiff1d(np.arange(I), used)
+        assert np.array_equal(m1[j][unused], z[p + "m0"][unused]) and np.array_equal(q1[j][unused], z[p + "q0"][unused])
+        np.testing.assert_array_equal(mp[j], m1[j])  # update_prior (Models.py:47-48)
+        np.testing.assert_allclose(sg[j], 1 / np.sqrt(q1[j]), rtol=1e-6)
+    eng.close()

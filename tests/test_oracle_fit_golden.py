@@ -6,6 +6,8 @@ Tolerances are the reference's own reproducibility floor (SURVEY.md section 0.6:
 fitted m by 8.8e-4 and the stop epoch by 5-11; an independent float32 restatement lands within +-18 epochs, |dm| 6e-3,
 q 6e-4): |dm| <= 1e-2, q <= 1e-3 rel, stop epoch +-1 % with a floor of 20 epochs.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -66,3 +68,19 @@ def test_winrate_fit_oracle_matches_the_reference(agent):
     g = np.linspace(0.1, 1.0, 64)
     x = np.stack([np.full(64, 0.12), np.full(64, 1.1), g], axis=1).astype(np.float32)
     np.testing.assert_allclose(ao.winrate32(orc["w"], x), ao.winrate32(ref_w, x), atol=2e-3, err_msg=what)
+
+
+@pytest.mark.parametrize("name", ["fit_ref_shape", "fit_64x64"])
+def test_newton_restatement_reaches_the_optimum_of_its_objective(name):
+    """oracle/fit_oracle.py::fit_allocator_newton restates the OPT-IN mode AGYM_FIT_NEWTON, which is not a reference algorithm:
+    the check is optimality on the reference-run fit inputs (gradient ~ 0, objective not above the reference's end point)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    for a in z["fit_agents"]:
+        p = f"it1_a{int(a)}_"
+        X, items, y = z[p + "X"], z[p + "items"], z[p + "y"]
+        r = fo.fit_allocator_newton(X, items, y, z[p + "m0"], z[p + "q0"], z[p + "m_prev"])
+        obj, grad = fo.allocator_objective(X, items, y, r["m"], z[p + "q0"], z[p + "m_prev"], prior_on_intercept=True)
+        obj_ref, _ = fo.allocator_objective(X, items, y, z[p + "m1"], z[p + "q0"], z[p + "m_prev"], prior_on_intercept=True)
+        assert np.abs(grad).max() < 5e-4 and obj <= obj_ref and r["passes"].max() <= 50, (name, p)
+        unused = np.setdiff1d(np.arange(len(z[p + "m0"])), np.unique(items))
+        assert np.array_equal(r["m"][unused], z[p + "m0"][unused]) and np.array_equal(r["q"][unused], z[p + "q0"][unused])
