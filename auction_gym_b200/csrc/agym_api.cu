@@ -31,6 +31,7 @@ SimParams make_params(const agym_handle* h) {
   p.n_items = h->d_n_items; p.alloc_kind = h->d_alloc_kind; p.bidder_kind = h->d_bidder_kind;
   p.E64 = h->d_E64; p.V64 = h->d_V64; p.E32 = h->d_E32; p.V32 = h->d_V32;
   p.m = h->m; p.sigma = h->sigma;
+  p.pk = h->pk_valid ? h->d_pk : nullptr; p.cat8 = h->d_cat8;
   p.bidder_d = h->bidder_d; p.bidder_w = h->bidder_w;
   p.acc = h->acc; p.revenue = h->revenue;
   p.fit_ctx = h->fit_ctx; p.fit_meta = h->fit_meta; p.Tcap = h->Tcap;
@@ -90,6 +91,7 @@ int agym_create(const agym_shape* shape, int device, agym_handle** out) {
             cudaMalloc(&h->d_bidder_kind, s.A * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_bidder_fit, s.A * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_E64, nE * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->d_V64, nV * sizeof(double)) == cudaSuccess && cudaMalloc(&h->d_E32, nE * sizeof(float)) == cudaSuccess &&
             cudaMalloc(&h->d_V32, nV * sizeof(float)) == cudaSuccess &&
+            (s.D != 5 || cudaMalloc(&h->d_cat8, nV * 2 * sizeof(float4)) == cudaSuccess) &&
             cudaMalloc(&h->d_adam_sz0, kAdamTable * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->d_adam_bc2s, kAdamTable * sizeof(float)) == cudaSuccess &&
             cudaMalloc(&h->d_adam_ep, kAdamTable * sizeof(float2)) == cudaSuccess &&
@@ -132,7 +134,7 @@ int agym_destroy(agym_handle* h) {
   if (!h) return AGYM_OK;
   DeviceGuard g(h->device);
   cudaFree(h->d_n_items); cudaFree(h->d_alloc_kind); cudaFree(h->d_bidder_kind); cudaFree(h->d_bidder_fit);
-  cudaFree(h->d_E64); cudaFree(h->d_V64); cudaFree(h->d_E32); cudaFree(h->d_V32);
+  cudaFree(h->d_E64); cudaFree(h->d_V64); cudaFree(h->d_E32); cudaFree(h->d_V32); cudaFree(h->d_cat8); cudaFree(h->d_pk);
   cudaFree(h->d_memory); cudaFree(h->d_mem_off);
   destroy_comm(h);
   cudaFree(h->d_fit_epochs); cudaFree(h->est_scratch);
@@ -209,6 +211,15 @@ int agym_set_catalog(agym_handle* h, const double* E, const double* V) {
   if (e == cudaSuccess) e = cudaMemcpy(h->d_V64, V, nV * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_E32, e32.data(), nE * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_V32, v32.data(), nV * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && h->d_cat8) {  // D == 5: {e0 e1 e2 e3} {e4 e5 V 0} per item
+    std::vector<float4> c8(nV * 2);
+    for (size_t i = 0; i < nV; ++i) {
+      const float* r = &e32[i * 6];
+      c8[2 * i] = make_float4(r[0], r[1], r[2], r[3]);
+      c8[2 * i + 1] = make_float4(r[4], r[5], v32[i], 0.f);
+    }
+    e = cudaMemcpy(h->d_cat8, c8.data(), nV * 2 * sizeof(float4), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) return check_cuda(h, e, "agym_set_catalog");
   h->catalog_set = true;
   return AGYM_OK;
@@ -217,6 +228,15 @@ int agym_set_catalog(agym_handle* h, const double* E, const double* V) {
 int agym_bind_allocator_state(agym_handle* h, float* m, float* q, float* m_prev, float* sigma) {
   if (!h || !m || !q || !m_prev || !sigma) return set_error(h, AGYM_ERR_INVALID, "agym_bind_allocator_state: null argument");
   h->m = m; h->q = q; h->m_prev = m_prev; h->sigma = sigma;
+  h->pk_valid = false;
+  if (h->shape.Do == 4 && h->shape.D == 5 && !h->d_pk) {  // standard shape: packed {m, 1/q} for the production round loop
+    DeviceGuard g(h->device);
+    const size_t n = (size_t)h->shape.R * h->shape.A * h->shape.I * 3;
+    if (cudaMalloc(&h->d_pk, n * sizeof(float4)) != cudaSuccess) {
+      h->d_pk = nullptr;
+      return set_error(h, AGYM_ERR_CUDA, std::string("agym_bind_allocator_state: cudaMalloc of the packed state failed: ") + cudaGetErrorString(cudaGetLastError()));
+    }
+  }
   return AGYM_OK;
 }
 
@@ -411,7 +431,8 @@ int agym_update_allocators(agym_handle* h, int32_t fit_mode, int32_t max_epochs,
   if (!h->m || !h->q || !h->m_prev || !h->sigma) return set_error(h, AGYM_ERR_STATE, "agym_update_allocators: allocator state not bound");
   if (!h->fit_ctx) return set_error(h, AGYM_ERR_STATE, "agym_update_allocators: fit log not bound");
   DeviceGuard g(h->device);
-  return launch_update_allocators(h, fit_mode, max_epochs, fit_info, (cudaStream_t)stream);
+  const int rc = launch_update_allocators(h, fit_mode, max_epochs, fit_info, (cudaStream_t)stream);
+  return rc ? rc : launch_pack_state(h, (cudaStream_t)stream);  // the round loop's packed copy of {m, 1/q} follows every update
 }
 
 static int staged_params(agym_handle* h, uint64_t seed, int32_t iter, int64_t T, SimParams* p, const char* who) {

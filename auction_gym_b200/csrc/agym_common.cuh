@@ -45,6 +45,11 @@ struct SimParams {
   // learnt allocator state [R][A][I][K]
   const float* m;
   const float* sigma;
+  // production-mode copies for the standard shape (D = 5, Do = 4), 128-bit loads; null when not applicable / not current:
+  //   pk   [R][A][I][3] float4  {m0 m1 m2 m3} {1/q0 1/q1 1/q2 1/q3} {m4 1/q4 0 0}   (written by pack_state_kernel)
+  //   cat8 [A][I][2]    float4  {e0 e1 e2 e3} {e4 e5 V 0}                           (written by agym_set_catalog)
+  const float4* pk;
+  const float4* cat8;
   // bidder state
   const double* bidder_d;  // [R][A][AGYM_BIDDER_D]
   const float* bidder_w;   // [R][A][AGYM_BIDDER_W]
@@ -198,6 +203,9 @@ struct agym_handle {
   double* d_V64 = nullptr;
   float* d_E32 = nullptr;
   float* d_V32 = nullptr;
+  float4* d_cat8 = nullptr;  // packed float catalog (D == 5)
+  float4* d_pk = nullptr;    // packed {m, 1/q} (Do == 4), current while pk_valid
+  bool pk_valid = false;
   double* d_adam_bc1 = nullptr;  // [kAdamTable2] 1 - 0.9^t
   float* d_adam_bc2s2 = nullptr; // [kAdamTable2] sqrt(1 - 0.999^t)
   double* d_adam_sz0 = nullptr;  // [kAdamTable] 2e-3 / (1 - 0.9^t), t = epoch + 1 (torch Adam step size at lr 2e-3)
@@ -256,6 +264,7 @@ SimParams make_params(const agym_handle* h);
 // kernels' host launchers (one per translation unit)
 int launch_simulate(agym_handle* h, const SimParams& p, const agym_replay_inputs* in, const agym_round_log* log, cudaStream_t s);
 int launch_refresh_sigma(agym_handle* h, cudaStream_t s);
+int launch_pack_state(agym_handle* h, cudaStream_t s);  // rebuilds SimParams::pk from m and q (no-op for other shapes)
 int launch_retain_logs(agym_handle* h, cudaStream_t s);
 int clear_retained_rows(agym_handle* h, cudaStream_t s);
 int launch_update_allocators(agym_handle* h, int fit_mode, int max_epochs, float* fit_info, cudaStream_t s);

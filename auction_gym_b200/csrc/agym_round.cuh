@@ -83,11 +83,81 @@ __device__ __forceinline__ void draw_participants_thread(int P, int A, RoundCoun
   }
 }
 
+template <typename Real, bool kReplay>
+constexpr bool kPackedOk = false;
+template <>
+constexpr bool kPackedOk<float, false> = true;
+
 template <typename Real>
 struct SlotEval {
   int item;
   Real est, true_sel, value, best_ev;
 };
+
+// ---- production path of the standard shape (embedding_size 5, obs_embedding_size 4, float): packed 128-bit loads and
+// single-instruction MUFU approximations.  Never used in replay mode or FP64, i.e. nowhere parity is claimed. ----
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_approx(float z) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * z)); }
+__device__ __forceinline__ float2 box_muller_approx(uint32_t a, uint32_t b) {
+  const float r = sqrt_approx(-1.3862943611198906f * lg2_approx(u32_to_unit_open0(a)));  // sqrt(-2 ln u), u in (0, 1]
+  float sn, cs;
+  __sincosf(6.283185307179586f * u32_to_unit(b), &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+// true CTR of item i for context x (Auction.py:52); the item loop and the chosen item's record share this exact sequence,
+// so the allocation regret best - chosen can never come out negative
+__device__ __forceinline__ float true_ctr_packed(const float4 ea, const float4 eb, const float (&x)[5]) {
+  float z = fmaf(x[0], ea.x, eb.y);
+  z = fmaf(x[1], ea.y, z);
+  z = fmaf(x[2], ea.z, z);
+  z = fmaf(x[3], ea.w, z);
+  z = fmaf(x[4], eb.x, z);
+  return sigmoid_approx(z);
+}
+
+// Item scores of one participant over the lanes of its group: four items per lane and pass (one Philox block = two
+// Box-Muller pairs = their four Thompson normals, as in the generic loop: the noise of an item does not depend on the path).
+template <int G>
+__device__ __forceinline__ void eval_items_packed(const SimParams& p, int run, int a, int s, const float (&x)[5], bool ts, RoundCounter rc,
+                                                  PhiloxKey key, int lane, float& bscore, int& bi, float& btv) {
+  const int I = p.I, nI = p.n_items[a];
+  const float4* __restrict__ cat = p.cat8 + (size_t)a * I * 2;
+  const float4* __restrict__ pk = p.pk + ((size_t)run * p.A + a) * I * 3;
+  const float xx0 = x[0] * x[0], xx1 = x[1] * x[1], xx2 = x[2] * x[2], xx3 = x[3] * x[3];
+  for (int i0 = lane; i0 < nI; i0 += 4 * G) {
+    float nz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ts) {
+      const uint4 b = philox4x32_10(rc.c0, rc.c1, (kPurposeTS << 16) | uint32_t(s), uint32_t(i0), key);
+      const float2 n01 = box_muller_approx(b.x, b.y), n23 = box_muller_approx(b.z, b.w);
+      nz[0] = n01.x; nz[1] = n01.y; nz[2] = n23.x; nz[3] = n23.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * G;
+      if (i < nI) {
+        const float4 ea = cat[2 * i], eb = cat[2 * i + 1];
+        const float4 ma = pk[3 * i], va = pk[3 * i + 1], mb = pk[3 * i + 2];
+        const float tv = true_ctr_packed(ea, eb, x) * eb.z;
+        btv = fmaxf(btv, tv);
+        float zl = fmaf(x[0], ma.x, mb.x);
+        zl = fmaf(x[1], ma.y, zl);
+        zl = fmaf(x[2], ma.z, zl);
+        zl = fmaf(x[3], ma.w, zl);
+        // logit-space Thompson draw: sum_k (m_k + eps_k sigma_k) x_k ~ N(m.x, sum_k sigma_k^2 x_k^2) (Models.py:31)
+        float var = fmaf(xx0, va.x, mb.y);
+        var = fmaf(xx1, va.y, var);
+        var = fmaf(xx2, va.z, var);
+        var = fmaf(xx3, va.w, var);
+        zl = fmaf(sqrt_approx(var), nz[j], zl);
+        const float score = sigmoid_approx(zl) * eb.z;  // Agent.py:33
+        if (score > bscore) { bscore = score; bi = i; }
+      }
+    }
+  }
+}
 
 // Agent.select_item + the true-CTR bookkeeping of Auction.py:52-53 for the agent in slot s.
 // Lanes of the group stride over the agent's items; the result is uniform across the group.
@@ -110,7 +180,18 @@ __device__ __forceinline__ SlotEval<Real> eval_slot(const SimParams& p, int run,
   int bi = INT_MAX;
   uint4 ts_bits = make_uint4(0u, 0u, 0u, 0u);
   float2 ts_pair = make_float2(0.f, 0.f);
-  for (int i = lane; i < nI; i += G) {
+  // production, float, standard shape, learnt allocator, packed copies current: the 128-bit path
+  const bool packed = kPackedOk<Real, kReplay> && D == 5 && Do == 4 && akind != AGYM_ALLOC_ORACLE && p.pk != nullptr && p.cat8 != nullptr;
+  float px[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (packed) {
+#pragma unroll
+    for (int d = 0; d < 5; ++d) px[d] = float(ctx[d < DMAX ? d : 0]);
+    float fs = -INFINITY, ft = -INFINITY;
+    eval_items_packed<G>(p, run, a, s, px, akind == AGYM_ALLOC_TS, rc, key, lane, fs, bi, ft);
+    bscore = Real(fs);
+    btv = Real(ft);
+  }
+  for (int i = lane; i < (packed ? 0 : nI); i += G) {
     const Real* __restrict__ e = Ea + (size_t)i * (D + 1);
     Real z = 0;
 #pragma unroll
@@ -184,6 +265,22 @@ __device__ __forceinline__ SlotEval<Real> eval_slot(const SimParams& p, int run,
     btv = ot > btv ? ot : btv;
   }
   if (bi == INT_MAX) bi = 0;
+  if (packed) {  // chosen item through the same loads and the same true-CTR sequence as the loop
+    const float4* __restrict__ cat = p.cat8 + ((size_t)a * I + bi) * 2;
+    const float4* __restrict__ pk = p.pk + (((size_t)run * p.A + a) * I + bi) * 3;
+    const float4 ea = cat[0], eb = cat[1], ma = pk[0], mb = pk[2];
+    float zl = fmaf(px[0], ma.x, mb.x);
+    zl = fmaf(px[1], ma.y, zl);
+    zl = fmaf(px[2], ma.z, zl);
+    zl = fmaf(px[3], ma.w, zl);
+    SlotEval<Real> r;
+    r.item = bi;
+    r.true_sel = Real(true_ctr_packed(ea, eb, px));
+    r.est = Real(sigmoid_approx(zl));  // MAP estimate of the chosen item (Agent.py:38-42)
+    r.value = Real(eb.z);
+    r.best_ev = btv;
+    return r;
+  }
   // chosen item: true CTR and the estimate that is logged and bid on (Agent.py:38-42)
   const Real* __restrict__ e = Ea + (size_t)bi * (D + 1);
   Real z = 0;

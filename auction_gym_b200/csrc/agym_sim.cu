@@ -252,12 +252,37 @@ __global__ void refresh_sigma_kernel(const float* __restrict__ q, float* __restr
   if (i < n) sigma[i] = __fdiv_rn(1.0f, __fsqrt_rn(q[i]));  // Models.py:31  1.0/torch.sqrt(q)
 }
 
+// Standard shape (K = 5): one record of three float4 per (run, agent, item) so that the production round loop reads an
+// item's posterior with 128-bit loads: {m0 m1 m2 m3} {v0 v1 v2 v3} {m4 v4 0 0}, v = 1 / q = sigma^2 (Models.py:31).
+__global__ void pack_state_kernel(const float* __restrict__ m, const float* __restrict__ q, float4* __restrict__ pk, size_t n_items) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  const float* __restrict__ mi = m + i * 5;
+  const float* __restrict__ qi = q + i * 5;
+  float v[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) v[k] = __fdiv_rn(1.0f, qi[k]);
+  pk[3 * i] = make_float4(mi[0], mi[1], mi[2], mi[3]);
+  pk[3 * i + 1] = make_float4(v[0], v[1], v[2], v[3]);
+  pk[3 * i + 2] = make_float4(mi[4], v[4], 0.f, 0.f);
+}
+
+int launch_pack_state(agym_handle* h, cudaStream_t s) {
+  if (!h->d_pk || !h->m || !h->q) return AGYM_OK;
+  const size_t n = (size_t)h->shape.R * h->shape.A * h->shape.I;
+  pack_state_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(h->m, h->q, h->d_pk, n);
+  h->launches += 1;
+  h->pk_valid = true;
+  return check_cuda(h, cudaGetLastError(), "pack_state_kernel");
+}
+
 int launch_refresh_sigma(agym_handle* h, cudaStream_t s) {
   if (!h->q || !h->sigma) return set_error(h, AGYM_ERR_STATE, "agym_refresh_sigma: allocator state not bound");
   const size_t n = (size_t)h->shape.R * h->shape.A * h->shape.I * h->K;
   refresh_sigma_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(h->q, h->sigma, n);
   h->launches += 1;
-  return check_cuda(h, cudaGetLastError(), "refresh_sigma");
+  const int rc = check_cuda(h, cudaGetLastError(), "refresh_sigma");
+  return rc ? rc : launch_pack_state(h, s);
 }
 
 template <typename Real, int G, int DMAX>

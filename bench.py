@@ -627,7 +627,7 @@ def main():
                         "note": "same iterations of the same trajectory as `value` (restart from the initial host state, same warm-up); every step "
                                 "uploads the learnt state from pinned host memory and reads state + metrics back"},
                 "gpu_launches": int(launches), "gpu_launches_note": "agym_launch_count difference over the timed region on rank 0 (sim_kernel, bucket_kernel, "
-                                                                     "fit_classify_kernel, fit_order_kernel, two fit_warp_kernel instantiations per step and sub-shard)",
+                                                                     "fit_classify_kernel, fit_order_kernel, two fit_warp_kernel instantiations, pack_state_kernel per step and sub-shard)",
                 "subshards": NS,
                 "round_loop": {"value": runs_job * T / k_ms["rounds"] * 1e3 if k_ms["rounds"] else None, "unit": UNIT, "ms": k_ms["rounds"]},
                 "full_workload": full, "opt_in_newton_mode": newton,

@@ -142,7 +142,9 @@ int agym_set_catalog(agym_handle* h, const double* E, const double* V);
 /* ---- device state owned by the caller (device pointers, borrowed until re-bound / destroy) ---- */
 /* learnt allocator state: m, q, m_prev, sigma = 1/sqrt(q)   each [R][A][I][K] float  (Models.py:21-24) */
 int agym_bind_allocator_state(agym_handle* h, float* m, float* q, float* m_prev, float* sigma);
-int agym_refresh_sigma(agym_handle* h, void* stream);  /* sigma <- 1/sqrt(q) after q was written by the host */
+/* Call after the HOST wrote m or q: sigma <- 1/sqrt(q) (Models.py:31), and the library's packed copy of {m, 1/q} that the
+ * production round loop reads with 128-bit loads is rebuilt (agym_update_allocators does both itself). */
+int agym_refresh_sigma(agym_handle* h, void* stream);
 /* bidder state: bidder_d [R][A][AGYM_BIDDER_D] double, bidder_w [R][A][AGYM_BIDDER_W] float */
 int agym_bind_bidder_state(agym_handle* h, double* bidder_d, float* bidder_w);
 /* accumulators: acc [R][A][AGYM_NUM_METRICS] double, revenue [R] double  (Agent.py:20-21, Auction.py:16) */
