@@ -14,8 +14,11 @@
 
 namespace agym {
 
+#ifndef AGYM_SIM_MINB
+#define AGYM_SIM_MINB 3
+#endif
 template <typename Real, int G, int DMAX, bool kReplay, int DT, int DoT, bool kMulti>
-__global__ void __launch_bounds__(256, DT > 0 ? 3 : 1) sim_kernel(const SimParams p, const agym_replay_inputs in, const agym_round_log log) {
+__global__ void __launch_bounds__(256, DT > 0 ? AGYM_SIM_MINB : 1) sim_kernel(const SimParams p, const agym_replay_inputs in, const agym_round_log log) {
   using A_ = Arith<Real>;
   const int lane = threadIdx.x % G, group = threadIdx.x / G, ngroups = blockDim.x / G;
   const int chunks = int((p.T + p.chunk - 1) / p.chunk);
