@@ -79,6 +79,7 @@ SIGNATURES = {
     "agym_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "agym_comm_init": (C.c_int, [_H, C.c_char_p, C.c_int32, C.c_int32]),
     "agym_gather_metrics_nccl": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "agym_gather_block_nccl": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "agym_launch_count": (C.c_uint64, [_H]),
     "agym_set_option": (C.c_int, [_H, C.c_char_p, C.c_double]),
     "agym_update_allocators": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

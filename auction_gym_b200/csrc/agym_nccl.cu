@@ -109,4 +109,13 @@ int agym_gather_metrics_nccl(agym_handle* h, double* recv_acc, double* recv_reve
   return AGYM_OK;
 }
 
+int agym_gather_block_nccl(agym_handle* h, const double* send, double* recv, int64_t count, void* stream) {
+  if (!h || !send || !recv || count < 0) return agym::set_error(h, AGYM_ERR_INVALID, "agym_gather_block_nccl: bad argument");
+  if (!h->nccl_comm) return agym::set_error(h, AGYM_ERR_STATE, "agym_gather_block_nccl: call agym_comm_init first");
+  if (count == 0) return AGYM_OK;
+  const int rc = nccl().AllGather(send, recv, (size_t)count, kNcclFloat64, h->nccl_comm, (cudaStream_t)stream);
+  if (rc) return nccl_fail(h, rc, "agym_gather_block_nccl");
+  return AGYM_OK;
+}
+
 }  // extern "C"

@@ -430,6 +430,21 @@ class Engine:
         self.gathered_acc = torch.empty((self.comm_world, self.R, self.A, _lib.NUM_METRICS), dtype=torch.float64, device=self.device)
         self.gathered_revenue = torch.empty((self.comm_world, self.R), dtype=torch.float64, device=self.device)
 
+    def swap_metrics(self):
+        """Double-buffered accumulators: bind the spare (acc, revenue) pair for the next iteration and return the pair that
+        holds the iteration just finished, so that its read-out (copy to the host, all-gather) can run on another stream
+        while the next iteration computes.  The caller orders the reuse of a pair after its read-out (events).  Not with log
+        retention, whose accumulators carry over between iterations."""
+        if self.retention:
+            raise AgymError("swap_metrics: not available with log retention (the accumulators carry retained records)")
+        done = (self.acc, self.revenue)
+        if getattr(self, "_spare_metrics", None) is None:
+            self._spare_metrics = (torch.zeros_like(self.acc), torch.zeros_like(self.revenue))
+        self.acc, self.revenue = self._spare_metrics
+        self._spare_metrics = done
+        self._check(self.lib.agym_bind_metrics(self.handle, _ptr(self.acc), _ptr(self.revenue)))
+        return done
+
     def gather_metrics(self):
         """All-gather of every rank's accumulator block and revenue (agym_gather_metrics_nccl) on the current stream:
         returns device tensors [world, R, A, NUM_METRICS] and [world, R]."""
@@ -437,6 +452,17 @@ class Engine:
             raise AgymError("gather_metrics: call comm_init first")
         self._check(self.lib.agym_gather_metrics_nccl(self.handle, _ptr(self.gathered_acc), _ptr(self.gathered_revenue), self._stream()))
         return self.gathered_acc, self.gathered_revenue
+
+    def gather_block(self, block):
+        """All-gather of a float64 device tensor the caller kept (e.g. the metric blocks of every iteration of a job) through
+        agym_gather_block_nccl on the current stream: returns [world, *block.shape]."""
+        if not getattr(self, "comm_world", 0):
+            raise AgymError("gather_block: call comm_init first")
+        if block.dtype != torch.float64 or not block.is_contiguous() or not block.is_cuda:
+            raise AgymError("gather_block: needs a contiguous float64 device tensor")
+        out = torch.empty((self.comm_world,) + tuple(block.shape), dtype=torch.float64, device=block.device)
+        self._check(self.lib.agym_gather_block_nccl(self.handle, _ptr(block), _ptr(out), block.numel(), self._stream()))
+        return out
 
     # ------------------------------------------------------------------ results
     def metrics(self):

@@ -85,7 +85,7 @@ def config_dict(args, world, runs_job, scaling, first_it, n_it):
             "runs": runs_job, "runs_per_gpu": runs_job // world, "rounds_per_step": args.rounds, "iterations": [first_it, first_it + n_it],
             "agents": w["A"], "items": w["I"], "embedding_size": w["D"], "obs_embedding_size": w["Do"],
             "participants": w["P"], "allocation": "SecondPrice", "allocator": args.allocator, "fit_mode": args.fit_mode,
-            "step": "one iteration: T rounds (fused K1-K5) + allocator fits (K6) + metric read-out" + (" + NCCL all-gather of the metric block (K8)" if world > 1 else ""),
+            "step": "one iteration: T rounds (fused K1-K5) + allocator fits (K6) + metric read-out to the host" + ("; the timed region ends with ONE NCCL all-gather of the metric blocks of all its iterations (K8, agym_gather_block_nccl), as main.py:186-222 assembles its per-run rows once the runs have finished" if world > 1 else ""),
             "parallelism": f"runs sharded over {world} GPU(s) ({scaling} scaling), no data-path collective" +
                            (f"; each GPU's runs go as {args.subshards} independent sub-shards on {args.subshards} CUDA streams, so the tail of one "
                             f"sub-shard's fit grid overlaps the other's kernels (runs are independent, main.py:186-189; results are bit-identical)"
@@ -301,7 +301,8 @@ def main():
     learnt = args.allocator == "ts"
     fit_mode = {"adam_ref": _lib.FIT_ADAM_REF, "adam_fast": _lib.FIT_ADAM_FAST, "newton": _lib.FIT_NEWTON}[args.fit_mode]
     if args.subshards <= 0:
-        args.subshards = 2 if (R <= 2048 and R % 2 == 0 and learnt) else 1
+        # measured on B200, 512 runs per GPU, whole trajectory: 1 / 2 / 4 sub-shards -> 4.60 / 4.20 / 4.16 s
+        args.subshards = (4 if (R <= 512 and R % 4 == 0) else 2 if (R <= 2048 and R % 2 == 0) else 1) if learnt else 1
     NS = args.subshards
     assert R % NS == 0, "--subshards must divide the runs per GPU"
     Rs = R // NS
@@ -327,6 +328,10 @@ def main():
         if world > 1:
             sb.eng.comm_init(rank, world)  # this sub-shard's NCCL communicator (agym_comm_init; the id is broadcast by torch.distributed)
         sb.epochs_sum = torch.zeros(2, dtype=torch.float64, device=dev)  # {sum of epochs, fits} over the steps that ask for it
+        if world > 1:  # the metric blocks of a region's iterations, kept for the one all-gather at its end
+            n_hist = max(args.steps, args.full_iterations)
+            sb.hist_acc = torch.zeros((n_hist, Rs, A, _lib.NUM_METRICS), dtype=torch.float64, device=dev)
+            sb.hist_rev = torch.zeros((n_hist, Rs), dtype=torch.float64, device=dev)
         subs.append(sb)
     eng = subs[0].eng
     stream = torch.cuda.current_stream(dev)
@@ -337,13 +342,24 @@ def main():
         if world > 1:
             dist.barrier(device_ids=[local_rank])
 
-    def read_out(sb):
-        """Per-iteration metric read-out: D2H of this rank's block; at N > 1 also the NCCL all-gather (K8)."""
+    def read_out(sb, slot=None):
+        """Per-iteration metric read-out: D2H of this rank's block.  `slot`: the block is also kept on the device for the job's
+        one collective (gather_history: main.py:186-222 assembles its per-run rows once, when the runs have finished)."""
         e = sb.eng
-        if world > 1:
-            e.gather_metrics()  # agym_gather_metrics_nccl: ncclAllGather of the [Rs, A, 12] block and the revenue on this stream
         sb.acc_host.copy_(e.acc, non_blocking=True)
         sb.rev_host.copy_(e.revenue, non_blocking=True)
+        if slot is not None and world > 1:
+            sb.hist_acc[slot].copy_(e.acc)
+            sb.hist_rev[slot].copy_(e.revenue)
+
+    def gather_history(n_slots):
+        """K8 inside the timed region: ONE NCCL all-gather per sub-shard of the metric blocks of the region's n_slots iterations
+        ([n, Rs, A, 12] and [n, Rs] doubles, agym_gather_block_nccl), on the sub-shard's stream."""
+        if world == 1:
+            return
+        for sb in subs:
+            with torch.cuda.stream(sb.stream):
+                sb.gathered = (sb.eng.gather_block(sb.hist_acc[:n_slots]), sb.eng.gather_block(sb.hist_rev[:n_slots]))
 
     def step_device(it, timed, count_epochs=False):
         """One iteration with everything resident in HBM (every sub-shard on its own stream)."""
@@ -366,7 +382,7 @@ def main():
                     e2.record(sb.stream)
                     ev_pairs["rounds"].append((e0, e1))
                     ev_pairs["fit"].append((e1, e2))
-                read_out(sb)
+                read_out(sb, slot=(it - args.warmup) if timed else None)
 
     def step_e2e(it):
         """The same iteration through the public API with HOST buffers: learnt state up, metrics + state down."""
@@ -382,7 +398,7 @@ def main():
                     sb.m_host.copy_(e.m, non_blocking=True)
                     sb.q_host.copy_(e.q, non_blocking=True)
                     sb.mp_host.copy_(e.m_prev, non_blocking=True)
-                read_out(sb)
+                read_out(sb, slot=(it - args.warmup) if it >= args.warmup else None)
         for sb in subs:  # the step's result is on the host before the next step starts
             sb.stream.synchronize()
 
@@ -404,6 +420,7 @@ def main():
         fork_streams()
         for i in range(steps):
             fn(it0 + i)
+        gather_history(steps)  # K8: the region's one collective, inside the region
         join_streams()
         e.record(stream)
         torch.cuda.synchronize(dev)
@@ -424,6 +441,7 @@ def main():
     # ---- warm-up, then the device-resident timed region: iterations W .. W+K-1 ----
     for it in range(args.warmup):
         step_device(it, False, count_epochs=True)  # same code path as the timed steps (no first-call costs inside the timed region)
+    gather_history(1)  # ... including the collective's first call
     torch.cuda.synchronize(dev)
     for sb in subs:
         sb.epochs_sum.zero_()
@@ -477,11 +495,12 @@ def main():
                         info = sb.eng.update_allocators(want_info=True, fit_mode=mode)
                         ran = info[..., 1]
                         acc_ep.append(torch.stack([ran.sum(dtype=torch.float64), (ran > 0).sum().to(torch.float64)]))
-                    read_out(sb)
+                    read_out(sb, slot=it)
             if learnt:
                 info_keep.append(acc_ep)
             b.record(subs[0].stream)
             per_it.append((a, b))
+        gather_history(n_full)
         join_streams()
         e_all.record(stream)
         torch.cuda.synchronize(dev)
@@ -508,7 +527,7 @@ def main():
     if not args.no_full:
         full = trajectory(args.full_iterations, fit_mode)
         full.update(target={"value": 1e9, "n_gpus": 8, "source": "BASELINE.json north_star"},
-                    note="whole job, max over ranks, device-resident state, per-iteration metric read-out (and all-gather at N > 1) included")
+                    note="whole job, max over ranks, device-resident state, per-iteration metric read-out and (N > 1) the one all-gather of all iterations' metric blocks included")
         if learnt and fit_mode != _lib.FIT_NEWTON:
             newton = trajectory(args.full_iterations, _lib.FIT_NEWTON)
             newton.update(fit_mode="newton", fit_passes_mean_per_iteration=newton.pop("fit_epochs_mean_per_iteration"),

@@ -214,6 +214,10 @@ int agym_estimate_ctr(agym_handle* h, int32_t run, int32_t agent, const double* 
 int agym_nccl_unique_id(char* out128);
 int agym_comm_init(agym_handle* h, const char* id128, int32_t rank, int32_t world);
 int agym_gather_metrics_nccl(agym_handle* h, double* recv_acc, double* recv_revenue, void* stream);
+/* The same collective for a block the caller kept: `count` doubles at `send` (e.g. the metric blocks of all the iterations
+ * of a job, [N][R][A][AGYM_NUM_METRICS] -- main.py:186-222 assembles its per-run rows once, when the runs have finished)
+ * are all-gathered into recv [world][count] on `stream`. */
+int agym_gather_block_nccl(agym_handle* h, const double* send, double* recv, int64_t count, void* stream);
 
 /* Number of kernels of this library launched through this handle so far (bench.py's gpu_launches is a difference of
  * two readings; the reference has no counterpart: it launches nothing). */

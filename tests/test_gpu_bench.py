@@ -31,7 +31,7 @@ def test_bench_line_carries_the_contract_keys():
     assert abs(d["value"] - opp / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
     e = d["e2e"]
     assert e["unit"] == d["unit"] and 0 < e["value"] <= d["value"] * 1.05 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
-    assert d["subshards"] == 2 and d["gpu_launches"] == 2 * 7 * d["subshards"]  # per sub-shard: sim_kernel, bucket_kernel, fit_classify_kernel, fit_order_kernel, fit_warp_kernel x 2, pack_state_kernel per step
+    assert d["subshards"] == 4 and d["gpu_launches"] == 2 * 7 * d["subshards"]  # per sub-shard: sim_kernel, bucket_kernel, fit_classify_kernel, fit_order_kernel, fit_warp_kernel x 2, pack_state_kernel per step
     assert d["config"]["iterations"] == [3, 5] and d["fit_epochs_mean"] > 1000
     f = d["full_workload"]
     assert f["iterations"] == 4 and len(f["ms_per_iteration"]) == 4 and len(f["fit_epochs_mean_per_iteration"]) == 4

@@ -343,4 +343,9 @@ def test_metric_gather_through_the_abi_single_rank():
     acc_g, rev_g = eng.gather_metrics()
     torch.cuda.synchronize()
     assert acc_g.shape == (1, 3, eng.A, _lib.NUM_METRICS) and torch.equal(acc_g[0], eng.acc) and torch.equal(rev_g[0], eng.revenue)
+    # a block the caller kept (all the iterations of a job): agym_gather_block_nccl
+    hist = torch.stack([eng.acc, 2 * eng.acc])
+    g = eng.gather_block(hist)
+    torch.cuda.synchronize()
+    assert g.shape == (1, 2, 3, eng.A, _lib.NUM_METRICS) and torch.equal(g[0], hist)
     eng.close()
