@@ -301,8 +301,9 @@ def main():
     learnt = args.allocator == "ts"
     fit_mode = {"adam_ref": _lib.FIT_ADAM_REF, "adam_fast": _lib.FIT_ADAM_FAST, "newton": _lib.FIT_NEWTON}[args.fit_mode]
     if args.subshards <= 0:
-        # measured on B200, 512 runs per GPU, whole trajectory: 1 / 2 / 4 sub-shards -> 4.60 / 4.20 / 4.16 s
-        args.subshards = (4 if (R <= 512 and R % 4 == 0) else 2 if (R <= 2048 and R % 2 == 0) else 1) if learnt else 1
+        # measured on B200, whole trajectory / e2e step: 512 runs per GPU, 1 / 2 / 4 sub-shards -> 4.60 / 4.20 / 4.16 s;
+        # 4096 runs per GPU -> 32.9 / 32.3 / 32.4 s and 555.9 / 532.0 / 524.5 ms (the copies of one sub-shard overlap the fits of another)
+        args.subshards = (4 if R % 4 == 0 else 2 if R % 2 == 0 else 1) if learnt else 1
     NS = args.subshards
     assert R % NS == 0, "--subshards must divide the runs per GPU"
     Rs = R // NS
@@ -566,8 +567,13 @@ def main():
     if not args.no_aux:
         # staged resolution kernel K4(+K5) on this GPU's resident runs: HBM-bound.  With the per-agent accumulation it moves
         # 13P + 10 = 36 B/opportunity; resolution + click alone never reads the values and agent ids: 8P + 10 = 26 B
-        Rk = Rs
+        # (all of them in ONE launch, whatever the sub-shard split of the timed steps: its own engine when NS > 1)
+        Rk = R
         engk = eng
+        if NS > 1:
+            engk = make_engine(ag, _lib, R, T, learnt, local_rank, first_run)
+            if learnt:
+                engk.set_allocator_state(initial_m(first_run, R))
         engk.clear_iteration()
         b = engk.staged_round(SEED, 0, T)
         flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)  # 4x the 126 MB L2
@@ -592,6 +598,8 @@ def main():
                 "bytes_per_opportunity": (13 * P + 10) if accumulate else (8 * P + 10),
                 "note": f"{Rk * T} opportunities, {by / 1e6:.0f} MB algorithmic; L2 flushed (512 MB fill) before every timed launch; outside the timed step"}
         del b, flush
+        if engk is not eng:
+            engk.close()
     dominant = max(kernels.items(), key=lambda kv: kv[1]["ms"])
     dprof = dominant[1].get("from_profile")
     roofline = {"kernel": dominant[0], "bound": "hbm", "achieved": dominant[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",

@@ -184,3 +184,42 @@ def test_device_philox_matches_restatement():
         want = np.stack([n0, n1, n2, n3, n4], axis=1)
         np.testing.assert_allclose(ctx[r], want, rtol=2e-5, atol=2e-6)
     eng.close()
+
+
+def test_packed_state_follows_every_write_of_the_learnt_state():
+    """Production mode of the standard shape reads the library's packed copy of {m, 1/q} (DESIGN.md, round loop).  The copy must
+    follow the learnt state through both doors: a host write (set_allocator_state -> agym_refresh_sigma) and the allocator update
+    (agym_update_allocators) -- an engine whose state went through them simulates exactly what a fresh engine holding the same
+    state simulates."""
+    gu = _gpu()
+    from auction_gym_b200 import _lib
+
+    case, *_ = load_golden("rounds_sp_ts_64x64")
+    R, T, seed = 2, 400, 77
+    rng = np.random.default_rng(5)
+    eng = gu.engine_from_case(case, R=R, precision=_lib.FP32, rounds_capacity=T)
+    a = _np(eng.simulate(seed, 0, T, FIELDS))
+    m2 = (np.broadcast_to(case["m"], (R,) + case["m"].shape) + 0.7 * rng.standard_normal((R,) + case["m"].shape)).astype(np.float32)
+    q2 = (1.0 + 3.0 * rng.random((R,) + case["m"].shape)).astype(np.float32)
+    eng.clear_iteration()
+    eng.set_allocator_state(m2, q2)
+    b = _np(eng.simulate(seed, 0, T, FIELDS))
+    assert not np.array_equal(a["item"], b["item"])  # the new state is the one that bids
+    fresh = gu.engine_from_case(case, R=R, precision=_lib.FP32, rounds_capacity=T)
+    fresh.set_allocator_state(m2, q2)
+    c = _np(fresh.simulate(seed, 0, T, FIELDS))
+    for k in FIELDS:
+        assert np.array_equal(b[k], c[k], equal_nan=True), k
+    # ... and through the update: iteration 1 from the fitted state
+    eng.update_allocators(max_epochs=60, want_info=False)
+    m3, q3 = eng.m.cpu().numpy().copy(), eng.q.cpu().numpy().copy()
+    assert not np.array_equal(m3, m2)
+    eng.clear_iteration()
+    d = _np(eng.simulate(seed, 1, T, FIELDS))
+    fresh.clear_iteration()
+    fresh.set_allocator_state(m3, q3)
+    e = _np(fresh.simulate(seed, 1, T, FIELDS))
+    for k in FIELDS:
+        assert np.array_equal(d[k], e[k], equal_nan=True), k
+    eng.close()
+    fresh.close()
