@@ -598,6 +598,19 @@ def main():
                 "bytes_per_opportunity": (13 * P + 10) if accumulate else (8 * P + 10),
                 "note": f"{Rk * T} opportunities, {by / 1e6:.0f} MB algorithmic; L2 flushed (512 MB fill) before every timed launch; outside the timed step"}
         del b, flush
+        # the fused round loop alone, all resident runs in one launch, nothing else on the GPU (inside the timed steps the
+        # sub-shards' streams overlap, so the per-kernel intervals there are stretched by the other streams' kernels)
+        ts = []
+        for i in range(5):
+            engk.clear_iteration()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream); engk.simulate(SEED, args.warmup + i, T); e.record(stream)
+            torch.cuda.synchronize(dev)
+            ts.append(s.elapsed_time(e))
+        ms_r = float(np.mean(ts[2:]))
+        aux["round_loop_alone"] = {"ms": ms_r, "opportunities_per_s": Rk * T / ms_r * 1e3, "runs": Rk,
+                                   "bound": "issue / L1-L2 latency (see sim_kernel)", "from_profile": profile_numbers(r"sim_kernel", None),
+                                   "note": "sim_kernel on all resident runs, one launch, alone on the GPU, outside the timed step"}
         if engk is not eng:
             engk.close()
     dominant = max(kernels.items(), key=lambda kv: kv[1]["ms"])
@@ -656,7 +669,10 @@ def main():
                 "gpu_launches": int(launches), "gpu_launches_note": "agym_launch_count difference over the timed region on rank 0 (sim_kernel, bucket_kernel, "
                                                                      "fit_classify_kernel, fit_order_kernel, two fit_warp_kernel instantiations, pack_state_kernel per step and sub-shard)",
                 "subshards": NS,
-                "round_loop": {"value": runs_job * T / k_ms["rounds"] * 1e3 if k_ms["rounds"] else None, "unit": UNIT, "ms": k_ms["rounds"]},
+                "round_loop": ({"value": aux["round_loop_alone"]["opportunities_per_s"] * world, "unit": UNIT, "ms": aux["round_loop_alone"]["ms"],
+                                "note": "the fused round loop alone (roofline_kernels.round_loop_alone), per GPU x n_gpus"} if "round_loop_alone" in aux else
+                               {"value": runs_job * T / k_ms["rounds"] * 1e3 if k_ms["rounds"] else None, "unit": UNIT, "ms": k_ms["rounds"],
+                                "note": "CUDA-event interval inside the timed steps" + ("; stretched by the other sub-shards' kernels" if NS > 1 else "")}),
                 "full_workload": full, "opt_in_newton_mode": newton,
                 "roofline": roofline, "roofline_kernels": {**kernels, **aux}, "cpu_baseline": cpu, "shipped_config": shipped, "clocks": clk}
         print(json.dumps(line), flush=True)
