@@ -91,7 +91,7 @@ int agym_create(const agym_shape* shape, int device, agym_handle** out) {
             cudaMalloc(&h->d_bidder_kind, s.A * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_bidder_fit, s.A * sizeof(int)) == cudaSuccess && cudaMalloc(&h->d_E64, nE * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->d_V64, nV * sizeof(double)) == cudaSuccess && cudaMalloc(&h->d_E32, nE * sizeof(float)) == cudaSuccess &&
             cudaMalloc(&h->d_V32, nV * sizeof(float)) == cudaSuccess &&
-            (s.D != 5 || cudaMalloc(&h->d_cat8, nV * 2 * sizeof(float4)) == cudaSuccess) &&
+            (s.D != 5 || cudaMalloc(&h->d_cat8, (size_t)s.A * tiles_of(s.I) * kCatTile) == cudaSuccess) &&
             cudaMalloc(&h->d_adam_sz0, kAdamTable * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->d_adam_bc2s, kAdamTable * sizeof(float)) == cudaSuccess &&
             cudaMalloc(&h->d_adam_ep, kAdamTable * sizeof(float2)) == cudaSuccess &&
@@ -211,14 +211,19 @@ int agym_set_catalog(agym_handle* h, const double* E, const double* V) {
   if (e == cudaSuccess) e = cudaMemcpy(h->d_V64, V, nV * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_E32, e32.data(), nE * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(h->d_V32, v32.data(), nV * sizeof(float), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && h->d_cat8) {  // D == 5: {e0 e1 e2 e3} {e4 e5 V 0} per item
-    std::vector<float4> c8(nV * 2);
-    for (size_t i = 0; i < nV; ++i) {
-      const float* r = &e32[i * 6];
-      c8[2 * i] = make_float4(r[0], r[1], r[2], r[3]);
-      c8[2 * i + 1] = make_float4(r[4], r[5], v32[i], 0.f);
-    }
-    e = cudaMemcpy(h->d_cat8, c8.data(), nV * 2 * sizeof(float4), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && h->d_cat8) {  // D == 5: tiles of 8 items, [8 x {e0 e1 e2 e3}] [8 x {e4 e5 V 0}] (SimParams::cat8)
+    const int NT = tiles_of(s.I);
+    std::vector<float> c8((size_t)s.A * NT * (kCatTile / 4), 0.f);
+    for (int a = 0; a < s.A; ++a)
+      for (int i = 0; i < s.I; ++i) {
+        const float* r = &e32[((size_t)a * s.I + i) * 6];
+        float* t = &c8[((size_t)a * NT + i / kTile) * (kCatTile / 4)];
+        float* f0 = t + (i % kTile) * 4;
+        float* f1 = t + 32 + (i % kTile) * 4;
+        f0[0] = r[0]; f0[1] = r[1]; f0[2] = r[2]; f0[3] = r[3];
+        f1[0] = r[4]; f1[1] = r[5]; f1[2] = v32[(size_t)a * s.I + i]; f1[3] = 0.f;
+      }
+    e = cudaMemcpy(h->d_cat8, c8.data(), c8.size() * sizeof(float), cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) return check_cuda(h, e, "agym_set_catalog");
   h->catalog_set = true;
@@ -231,8 +236,8 @@ int agym_bind_allocator_state(agym_handle* h, float* m, float* q, float* m_prev,
   h->pk_valid = false;
   if (h->shape.Do == 4 && h->shape.D == 5 && !h->d_pk) {  // standard shape: packed {m, 1/q} for the production round loop
     DeviceGuard g(h->device);
-    const size_t n = (size_t)h->shape.R * h->shape.A * h->shape.I * 3;
-    if (cudaMalloc(&h->d_pk, n * sizeof(float4)) != cudaSuccess) {
+    const size_t bytes = (size_t)h->shape.R * h->shape.A * tiles_of(h->shape.I) * kPkTile;
+    if (cudaMalloc(&h->d_pk, bytes) != cudaSuccess) {
       h->d_pk = nullptr;
       return set_error(h, AGYM_ERR_CUDA, std::string("agym_bind_allocator_state: cudaMalloc of the packed state failed: ") + cudaGetErrorString(cudaGetLastError()));
     }
@@ -418,7 +423,7 @@ uint64_t agym_launch_count(const agym_handle* h) { return h ? h->launches : 0; }
 
 int agym_set_option(agym_handle* h, const char* name, double value) {
   if (!h || !name) return AGYM_ERR_INVALID;
-  static const char* const known[] = {"fit_dense", "fit_nt", "fit_ncap", "fit_warp", "fit_heavy", "sim_g", "bidfit_wide"};
+  static const char* const known[] = {"fit_dense", "fit_nt", "fit_ncap", "fit_warp", "fit_heavy", "sim_g", "sim_cat_smem", "bidfit_wide"};
   for (const char* k : known)
     if (std::string(k) == name) { h->options[name] = value; return AGYM_OK; }
   return set_error(h, AGYM_ERR_INVALID, std::string("agym_set_option: unknown option '") + name + "'");

@@ -28,6 +28,9 @@ __host__ __device__ inline int meta_agent(uint32_t m) { return int((m >> 12) & 0
 __host__ __device__ inline int meta_item(uint32_t m) { return int(m & 0xFFFu); }
 
 // Everything a round-loop kernel needs, passed by value.
+constexpr int kTile = 8, kPkTile = 320, kCatTile = 256;
+__host__ __device__ inline int tiles_of(int I) { return (I + kTile - 1) / kTile; }
+
 struct SimParams {
   int R, A, I, D, Do, K, P, mechanism;
   int max_slots;     // >= 1; rows of the winner log per round
@@ -45,11 +48,14 @@ struct SimParams {
   // learnt allocator state [R][A][I][K]
   const float* m;
   const float* sigma;
-  // production-mode copies for the standard shape (D = 5, Do = 4), 128-bit loads; null when not applicable / not current:
-  //   pk   [R][A][I][3] float4  {m0 m1 m2 m3} {1/q0 1/q1 1/q2 1/q3} {m4 1/q4 0 0}   (written by pack_state_kernel)
-  //   cat8 [A][I][2]    float4  {e0 e1 e2 e3} {e4 e5 V 0}                           (written by agym_set_catalog)
-  const float4* pk;
-  const float4* cat8;
+  // production-mode copies for the standard shape (D = 5, Do = 4), null when not applicable / not current.  Items go in tiles of
+  // kTile = 8, field-major inside a tile, so that the 8 lanes of a group read one field of items i .. i+7 as 128 contiguous
+  // bytes (16 sectors per warp request instead of the 32 of an array of records):
+  //   pk   per (run, agent), tiles_of(I) tiles of kPkTile = 320 B: [8 x float4 {m0 m1 m2 m3}] [8 x float4 {v0 v1 v2 v3}]
+  //        [8 x float2 {m4 v4}], v = 1 / q                                            (written by pack_state_kernel)
+  //   cat8 per agent, tiles of kCatTile = 256 B: [8 x float4 {e0 e1 e2 e3}] [8 x float4 {e4 e5 V 0}]   (agym_set_catalog)
+  const unsigned char* pk;
+  const unsigned char* cat8;
   // bidder state
   const double* bidder_d;  // [R][A][AGYM_BIDDER_D]
   const float* bidder_w;   // [R][A][AGYM_BIDDER_W]
@@ -203,8 +209,8 @@ struct agym_handle {
   double* d_V64 = nullptr;
   float* d_E32 = nullptr;
   float* d_V32 = nullptr;
-  float4* d_cat8 = nullptr;  // packed float catalog (D == 5)
-  float4* d_pk = nullptr;    // packed {m, 1/q} (Do == 4), current while pk_valid
+  unsigned char* d_cat8 = nullptr;  // tiled float catalog (D == 5), see SimParams
+  unsigned char* d_pk = nullptr;    // tiled {m, 1/q} (Do == 4), current while pk_valid
   bool pk_valid = false;
   double* d_adam_bc1 = nullptr;  // [kAdamTable2] 1 - 0.9^t
   float* d_adam_bc2s2 = nullptr; // [kAdamTable2] sqrt(1 - 0.999^t)
@@ -263,6 +269,9 @@ SimParams make_params(const agym_handle* h);
 
 // kernels' host launchers (one per translation unit)
 int launch_simulate(agym_handle* h, const SimParams& p, const agym_replay_inputs* in, const agym_round_log* log, cudaStream_t s);
+// Lane-group width of the round loop (one group per opportunity), the same for the fused and the staged kernels: the Thompson
+// noise of an item is addressed through its lane's position.  Option "sim_g" overrides the default (tests run every width).
+int sim_group_width(const agym_handle* h, int P, int DMAX);
 int launch_refresh_sigma(agym_handle* h, cudaStream_t s);
 int launch_pack_state(agym_handle* h, cudaStream_t s);  // rebuilds SimParams::pk from m and q (no-op for other shapes)
 int launch_retain_logs(agym_handle* h, cudaStream_t s);

@@ -107,6 +107,11 @@ __device__ __forceinline__ float2 box_muller_approx(uint32_t a, uint32_t b) {
   __sincosf(6.283185307179586f * u32_to_unit(b), &sn, &cs);
   return make_float2(r * cs, r * sn);
 }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
 // true CTR of item i for context x (Auction.py:52); the item loop and the chosen item's record share this exact sequence,
 // so the allocation regret best - chosen can never come out negative
 __device__ __forceinline__ float true_ctr_packed(const float4 ea, const float4 eb, const float (&x)[5]) {
@@ -123,12 +128,14 @@ __device__ __forceinline__ float true_ctr_packed(const float4 ea, const float4 e
 #endif
 // Item scores of one participant over the lanes of its group: four items per lane and pass (one Philox block = two
 // Box-Muller pairs = their four Thompson normals, as in the generic loop: the noise of an item does not depend on the path).
-template <int G>
+// kCatSm: the catalog tiles were staged in shared memory by the CTA (cat_sm = their shared-window address): they are static and
+// shared by every run, 128 KB at 64 x 64 items, and two of the five loads of an item.
+template <int G, bool kCatSm>
 __device__ __forceinline__ void eval_items_packed(const SimParams& p, int run, int a, int s, const float (&x)[5], bool ts, RoundCounter rc,
-                                                  PhiloxKey key, int lane, float& bscore, int& bi, float& btv) {
-  const int I = p.I, nI = p.n_items[a];
-  const float4* __restrict__ cat = p.cat8 + (size_t)a * I * 2;
-  const float4* __restrict__ pk = p.pk + ((size_t)run * p.A + a) * I * 3;
+                                                  PhiloxKey key, int lane, uint32_t cat_sm, float& bscore, int& bi, float& btv) {
+  const int nI = p.n_items[a], NT = tiles_of(p.I);
+  const unsigned char* __restrict__ cat = p.cat8 + (size_t)a * NT * kCatTile;
+  const unsigned char* __restrict__ pk = p.pk + ((size_t)run * p.A + a) * NT * kPkTile;
   const float xx0 = x[0] * x[0], xx1 = x[1] * x[1], xx2 = x[2] * x[2], xx3 = x[3] * x[3];
   for (int i0 = lane; i0 < nI; i0 += 4 * G) {
     float nz[4] = {0.f, 0.f, 0.f, 0.f};
@@ -150,8 +157,20 @@ __device__ __forceinline__ void eval_items_packed(const SimParams& p, int run, i
       const int i = i_raw;
       if (i < nI) {
 #endif
-        const float4 ea = cat[2 * i], eb = cat[2 * i + 1];
-        const float4 ma = pk[3 * i], va = pk[3 * i + 1], mb = pk[3 * i + 2];
+        // tile i / 8, position i % 8: the group's lanes read 128 (64) contiguous bytes per field
+        const unsigned char* ct = cat + (i >> 3) * kCatTile + (i & 7) * 16;
+        const unsigned char* pt = pk + (i >> 3) * kPkTile;
+        float4 ea, eb;
+        if (kCatSm) {
+          const uint32_t cs = cat_sm + uint32_t((a * NT + (i >> 3)) * kCatTile + (i & 7) * 16);
+          ea = lds128(cs);
+          eb = lds128(cs + 128);
+        } else {
+          ea = *reinterpret_cast<const float4*>(ct);
+          eb = *reinterpret_cast<const float4*>(ct + 128);
+        }
+        const float4 ma = *reinterpret_cast<const float4*>(pt + (i & 7) * 16), va = *reinterpret_cast<const float4*>(pt + 128 + (i & 7) * 16);
+        const float2 mb = *reinterpret_cast<const float2*>(pt + 256 + (i & 7) * 8);
         const float tv = ok ? true_ctr_packed(ea, eb, x) * eb.z : -INFINITY;
         btv = fmaxf(btv, tv);
         float zl = fmaf(x[0], ma.x, mb.x);
@@ -174,10 +193,10 @@ __device__ __forceinline__ void eval_items_packed(const SimParams& p, int run, i
 // Agent.select_item + the true-CTR bookkeeping of Auction.py:52-53 for the agent in slot s.
 // Lanes of the group stride over the agent's items; the result is uniform across the group.
 // DT / DoT > 0 fix embedding_size / obs_embedding_size at compile time (the shipped configs' 5 / 4), 0 = run time.
-template <typename Real, int G, int DMAX, bool kReplay, int DT = 0, int DoT = 0>
+template <typename Real, int G, int DMAX, bool kReplay, int DT = 0, int DoT = 0, bool kCatSm = false>
 __device__ __forceinline__ SlotEval<Real> eval_slot(const SimParams& p, int run, int a, int s, const Real (&ctx)[DMAX],
                                                     RoundCounter rc, PhiloxKey key, const float* __restrict__ ts_eps_slot,
-                                                    int lane) {
+                                                    int lane, uint32_t cat_sm = 0) {
   using A_ = Arith<Real>;
   const int D = DT > 0 ? DT : p.D, Do = DT > 0 ? DoT : p.Do, K = Do + 1, I = p.I;
   const int nI = p.n_items[a];
@@ -199,7 +218,7 @@ __device__ __forceinline__ SlotEval<Real> eval_slot(const SimParams& p, int run,
 #pragma unroll
     for (int d = 0; d < 5; ++d) px[d] = float(ctx[d < DMAX ? d : 0]);
     float fs = -INFINITY, ft = -INFINITY;
-    eval_items_packed<G>(p, run, a, s, px, akind == AGYM_ALLOC_TS, rc, key, lane, fs, bi, ft);
+    eval_items_packed<G, kCatSm>(p, run, a, s, px, akind == AGYM_ALLOC_TS, rc, key, lane, cat_sm, fs, bi, ft);
     bscore = Real(fs);
     btv = Real(ft);
   }
@@ -278,9 +297,20 @@ __device__ __forceinline__ SlotEval<Real> eval_slot(const SimParams& p, int run,
   }
   if (bi == INT_MAX) bi = 0;
   if (packed) {  // chosen item through the same loads and the same true-CTR sequence as the loop
-    const float4* __restrict__ cat = p.cat8 + ((size_t)a * I + bi) * 2;
-    const float4* __restrict__ pk = p.pk + (((size_t)run * p.A + a) * I + bi) * 3;
-    const float4 ea = cat[0], eb = cat[1], ma = pk[0], mb = pk[2];
+    const int NT = tiles_of(I);
+    const unsigned char* ct = p.cat8 + ((size_t)a * NT + (bi >> 3)) * kCatTile + (bi & 7) * 16;
+    const unsigned char* pt = p.pk + (((size_t)run * p.A + a) * NT + (bi >> 3)) * kPkTile;
+    float4 ea, eb;
+    if (kCatSm) {
+      const uint32_t cs = cat_sm + uint32_t((a * NT + (bi >> 3)) * kCatTile + (bi & 7) * 16);
+      ea = lds128(cs);
+      eb = lds128(cs + 128);
+    } else {
+      ea = *reinterpret_cast<const float4*>(ct);
+      eb = *reinterpret_cast<const float4*>(ct + 128);
+    }
+    const float4 ma = *reinterpret_cast<const float4*>(pt + (bi & 7) * 16);
+    const float2 mb = *reinterpret_cast<const float2*>(pt + 256 + (bi & 7) * 8);
     float zl = fmaf(px[0], ma.x, mb.x);
     zl = fmaf(px[1], ma.y, zl);
     zl = fmaf(px[2], ma.z, zl);

@@ -9,6 +9,7 @@
 //   charge / set_price / revenue and every per-agent metric (Agent.py:70-118, main.py:131-148).
 // The same body serves production mode (in-kernel Philox noise) and replay mode (host-drawn noise).
 #include <cstdlib>
+#include <type_traits>
 
 #include "agym_round.cuh"
 
@@ -17,9 +18,20 @@ namespace agym {
 #ifndef AGYM_SIM_MINB
 #define AGYM_SIM_MINB 3
 #endif
-template <typename Real, int G, int DMAX, bool kReplay, int DT, int DoT, bool kMulti>
-__global__ void __launch_bounds__(256, DT > 0 ? AGYM_SIM_MINB : 1) sim_kernel(const SimParams p, const agym_replay_inputs in, const agym_round_log log) {
+constexpr int kCatSmThreads = 768;  // one CTA per SM when the catalog is staged in shared memory: 24 warps, as 3 CTAs of 256 threads
+template <typename Real, int G, int DMAX, bool kReplay, int DT, int DoT, bool kMulti, bool kCatSm = false>
+__global__ void __launch_bounds__(kCatSm ? kCatSmThreads : 256, kCatSm ? 1 : (DT > 0 ? AGYM_SIM_MINB : 1))
+sim_kernel(const SimParams p, const agym_replay_inputs in, const agym_round_log log) {
   using A_ = Arith<Real>;
+  extern __shared__ __align__(16) unsigned char sim_smem[];
+  uint32_t cat_sm = 0;
+  if (kCatSm) {  // the static catalog tiles -> shared memory, once per CTA
+    const int n16 = p.A * tiles_of(p.I) * (kCatTile / 16);
+    const float4* __restrict__ src = reinterpret_cast<const float4*>(p.cat8);
+    for (int j = threadIdx.x; j < n16; j += blockDim.x) reinterpret_cast<float4*>(sim_smem)[j] = src[j];
+    __syncthreads();
+    cat_sm = uint32_t(__cvta_generic_to_shared(sim_smem));
+  }
   const int lane = threadIdx.x % G, group = threadIdx.x / G, ngroups = blockDim.x / G;
   const int chunks = int((p.T + p.chunk - 1) / p.chunk);
   const int rl = blockIdx.x / chunks, ck = blockIdx.x % chunks;
@@ -67,7 +79,7 @@ __global__ void __launch_bounds__(256, DT > 0 ? AGYM_SIM_MINB : 1) sim_kernel(co
     for (int s = 0; s < P; ++s) {
       const int a = shfl_idx<G>(my_agent, s);
       const float* eps_slot = (kReplay && in.ts_eps) ? in.ts_eps + ((size_t)ri * P + s) * p.I * (Do + 1) : nullptr;
-      const SlotEval<Real> ev = eval_slot<Real, G, DMAX, kReplay, DT, DoT>(p, run, a, s, ctx, rc, key, eps_slot, lane);
+      const SlotEval<Real> ev = eval_slot<Real, G, DMAX, kReplay, DT, DoT, kCatSm>(p, run, a, s, ctx, rc, key, eps_slot, lane, cat_sm);
       Real gamma, prop;
       int eff;
       Real bid = shade_bid<Real>(p, run, a, s, ev.value, ev.est, kReplay,
@@ -255,25 +267,33 @@ __global__ void refresh_sigma_kernel(const float* __restrict__ q, float* __restr
   if (i < n) sigma[i] = __fdiv_rn(1.0f, __fsqrt_rn(q[i]));  // Models.py:31  1.0/torch.sqrt(q)
 }
 
-// Standard shape (K = 5): one record of three float4 per (run, agent, item) so that the production round loop reads an
-// item's posterior with 128-bit loads: {m0 m1 m2 m3} {v0 v1 v2 v3} {m4 v4 0 0}, v = 1 / q = sigma^2 (Models.py:31).
-__global__ void pack_state_kernel(const float* __restrict__ m, const float* __restrict__ q, float4* __restrict__ pk, size_t n_items) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_items) return;
-  const float* __restrict__ mi = m + i * 5;
-  const float* __restrict__ qi = q + i * 5;
-  float v[5];
+// Standard shape (K = 5): the tiled copy of {m, 1 / q} the production round loop reads (layout: SimParams::pk), 1 / q =
+// sigma^2 (Models.py:31).  One thread per item slot of every (run, agent), padding slots of the last tile included.
+__global__ void pack_state_kernel(const float* __restrict__ m, const float* __restrict__ q, unsigned char* __restrict__ pk, int I, int NT,
+                                  size_t n_slots) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_slots) return;
+  const size_t ra = g / (size_t)(NT * kTile);       // (run, agent) pair
+  const int slot = int(g - ra * (size_t)(NT * kTile));
+  const int t = slot / kTile, pos = slot % kTile;
+  float mv[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (slot < I) {
+    const float* __restrict__ mi = m + (ra * I + slot) * 5;
+    const float* __restrict__ qi = q + (ra * I + slot) * 5;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) v[k] = __fdiv_rn(1.0f, qi[k]);
-  pk[3 * i] = make_float4(mi[0], mi[1], mi[2], mi[3]);
-  pk[3 * i + 1] = make_float4(v[0], v[1], v[2], v[3]);
-  pk[3 * i + 2] = make_float4(mi[4], v[4], 0.f, 0.f);
+    for (int k = 0; k < 5; ++k) { mv[k] = mi[k]; v[k] = __fdiv_rn(1.0f, qi[k]); }
+  }
+  unsigned char* tile = pk + (ra * NT + t) * (size_t)kPkTile;
+  *reinterpret_cast<float4*>(tile + pos * 16) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+  *reinterpret_cast<float4*>(tile + 128 + pos * 16) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float2*>(tile + 256 + pos * 8) = make_float2(mv[4], v[4]);
 }
 
 int launch_pack_state(agym_handle* h, cudaStream_t s) {
   if (!h->d_pk || !h->m || !h->q) return AGYM_OK;
-  const size_t n = (size_t)h->shape.R * h->shape.A * h->shape.I;
-  pack_state_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(h->m, h->q, h->d_pk, n);
+  const int NT = tiles_of(h->shape.I);
+  const size_t n = (size_t)h->shape.R * h->shape.A * NT * kTile;
+  pack_state_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(h->m, h->q, h->d_pk, h->shape.I, NT, n);
   h->launches += 1;
   h->pk_valid = true;
   return check_cuda(h, cudaGetLastError(), "pack_state_kernel");
@@ -290,12 +310,21 @@ int launch_refresh_sigma(agym_handle* h, cudaStream_t s) {
 
 template <typename Real, int G, int DMAX>
 static int launch_g(agym_handle* h, const SimParams& p, const agym_replay_inputs* in, const agym_round_log* log, cudaStream_t s) {
-  const int threads = 256;
+  const bool std_shape = DMAX == 8 && p.D == 5 && p.Do == 4;  // every shipped config and the bench shape
+  const bool multi = p.max_slots > 1;
+  // production, float, standard shape, packed state current, catalog small enough: stage the catalog tiles in shared memory
+  const size_t cat_bytes = (size_t)p.A * tiles_of(p.I) * kCatTile;
+  // -- OPT-IN (option "sim_cat_smem" 1), measured on B200 at the bench shape and not adopted: 8-lane groups 4.55 ms against 4.47 ms
+  // from global memory, 4-lane groups 4.52 against 4.06 (the catalog's lines are L1 hits anyway; one CTA of 768 threads per SM
+  // fills the tail of the grid worse than three of 256)
+  const bool cat_sm = std::is_same<Real, float>::value && G <= 8 && std_shape && !in && !multi && p.pk && p.cat8 && cat_bytes <= 160 * 1024 &&
+                      h->has_option("sim_cat_smem") && h->option("sim_cat_smem", 0) != 0;
+  const int threads = cat_sm ? kCatSmThreads : 256;
   const int ngroups = threads / G;
   SimParams q = p;
   // rounds per CTA: 16 per lane group, fewer when the launch is small so the grid still fills the SMs
   long long chunk = (long long)ngroups * 16;
-  while (chunk > ngroups && ((p.T + chunk - 1) / chunk) * p.n_runs < 4LL * h->num_sms) chunk /= 2;
+  while (chunk > ngroups && ((p.T + chunk - 1) / chunk) * p.n_runs < (cat_sm ? 2LL : 4LL) * h->num_sms) chunk /= 2;
   q.chunk = int(chunk);
   const long long chunks = (p.T + chunk - 1) / chunk;
   const long long grid = chunks * p.n_runs;
@@ -304,13 +333,21 @@ static int launch_g(agym_handle* h, const SimParams& p, const agym_replay_inputs
   agym_round_log lg = {};
   if (log) lg = *log;
   agym_replay_inputs ri = {};
-  const bool std_shape = DMAX == 8 && p.D == 5 && p.Do == 4;  // every shipped config and the bench shape
+  h->launches += 1;
+  if (cat_sm) {
+    if constexpr (std::is_same<Real, float>::value && G <= 8 && DMAX == 8) {
+      auto kern = sim_kernel<float, G, 8, false, 5, 4, false, true>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cat_bytes));
+      if (e != cudaSuccess) return check_cuda(h, e, "sim_kernel attribute");
+      kern<<<unsigned(grid), threads, cat_bytes, s>>>(q, ri, lg);
+      return check_cuda(h, cudaGetLastError(), "sim_kernel launch");
+    }
+  }
 #define AGYM_SIM(REPLAY, MULTI)                                                                                                   \
   do {                                                                                                                            \
     if (std_shape) sim_kernel<Real, G, DMAX, REPLAY, (DMAX == 8 ? 5 : 0), (DMAX == 8 ? 4 : 0), MULTI><<<unsigned(grid), threads, 0, s>>>(q, ri, lg); \
     else sim_kernel<Real, G, DMAX, REPLAY, 0, 0, MULTI><<<unsigned(grid), threads, 0, s>>>(q, ri, lg);                             \
   } while (0)
-  const bool multi = p.max_slots > 1;
   if (in) {
     ri = *in;
     if (multi) AGYM_SIM(true, true); else AGYM_SIM(true, false);
@@ -318,8 +355,22 @@ static int launch_g(agym_handle* h, const SimParams& p, const agym_replay_inputs
     if (multi) AGYM_SIM(false, true); else AGYM_SIM(false, false);
   }
 #undef AGYM_SIM
-  h->launches += 1;
   return check_cuda(h, cudaGetLastError(), "sim_kernel launch");
+}
+
+#ifndef AGYM_SIM_G
+#define AGYM_SIM_G 8
+#endif
+int sim_group_width(const agym_handle* h, int P, int DMAX) {
+  // 4 lanes per opportunity where the packed production path exists (float, standard shape, learnt allocators): everything
+  // outside the item loop is paid per warp instruction, i.e. per 8 opportunities instead of 4 (B200, bench shape: 4.47 -> 4.06 ms);
+  // the generic loop with its scalar loads prefers 8 (Oracle allocators: 3.56 ms against 4.34 with 4).  A property of the handle's
+  // configuration, never of a launch's size.
+  int G = (h->shape.precision == AGYM_FP32 && h->d_pk != nullptr) ? 4 : AGYM_SIM_G;
+  if (h->has_option("sim_g")) { const int v = int(h->option("sim_g", AGYM_SIM_G)); if (v == 4 || v == 8 || v == 16 || v == 32) G = v; }
+  while (G < P) G *= 2;
+  if (DMAX / 4 > G) G = 32;
+  return G;
 }
 
 template <typename Real, int DMAX>
@@ -329,11 +380,9 @@ static int launch_d(agym_handle* h, const SimParams& p, const agym_replay_inputs
   // opportunities per warp, more items per lane -- amortise it: B200, bench shape, G = 32 / 16 / 8 -> 10.6 / 7.7 / 7.2 ms
   // (Oracle allocators 6.1 / 4.7 / 3.6 ms).  The width is the same for every launch size (the Thompson noise of an item
   // is addressed through its lane's position, so a launch-size-dependent width would break "chunked calls == one call").
-  int G = 8;
-  if (h->has_option("sim_g")) { const int v = int(h->option("sim_g", 8)); if (v == 8 || v == 16 || v == 32) G = v; }  // tests: every width
-  while (G < p.P) G *= 2;
-  if (DMAX / 4 > G) G = 32;
+  const int G = sim_group_width(h, p.P, DMAX);
   switch (G) {
+    case 4: return launch_g<Real, 4, DMAX>(h, p, in, log, s);
     case 8: return launch_g<Real, 8, DMAX>(h, p, in, log, s);
     case 16: return launch_g<Real, 16, DMAX>(h, p, in, log, s);
     default: return launch_g<Real, 32, DMAX>(h, p, in, log, s);

@@ -89,13 +89,11 @@ template <int DMAX>
 static int launch_k2_d(agym_handle* h, const SimParams& p, const float* ctx, const uint8_t* parts, uint8_t* item, float* est,
                        float* true_ctr, float* best_ev, float* value, cudaStream_t s) {
   const long long N = (long long)p.R * p.T;
-  int G = 8;  // the fused kernel's lane-group width (agym_sim.cu launch_d): same Thompson noise addressing
-  if (h->has_option("sim_g")) { const int v = int(h->option("sim_g", 8)); if (v == 8 || v == 16 || v == 32) G = v; }
-  while (G < p.P) G *= 2;
-  if (DMAX / 4 > G) G = 32;
+  const int G = sim_group_width(h, p.P, DMAX);  // the fused kernel's lane-group width: same Thompson noise addressing
   const long long threads = N * G;
   const unsigned grid = unsigned((threads + 255) / 256);
-  if (G == 8) k2_kernel<8, DMAX><<<grid, 256, 0, s>>>(p, ctx, parts, item, est, true_ctr, best_ev, value, N);
+  if (G == 4) k2_kernel<4, DMAX><<<grid, 256, 0, s>>>(p, ctx, parts, item, est, true_ctr, best_ev, value, N);
+  else if (G == 8) k2_kernel<8, DMAX><<<grid, 256, 0, s>>>(p, ctx, parts, item, est, true_ctr, best_ev, value, N);
   else if (G == 16) k2_kernel<16, DMAX><<<grid, 256, 0, s>>>(p, ctx, parts, item, est, true_ctr, best_ev, value, N);
   else k2_kernel<32, DMAX><<<grid, 256, 0, s>>>(p, ctx, parts, item, est, true_ctr, best_ev, value, N);
   h->launches += 1;

@@ -225,7 +225,7 @@ uint64_t agym_launch_count(const agym_handle* h);
 
 /* Kernel-selection overrides for tests and experiments (the library never reads the environment): "fit_warp" 0 = CTA
  * fit kernels only, "fit_dense" 0/1, "fit_nt" threads per CTA, "fit_ncap" rows staged per fit as a multiple of the mean,
- * "fit_heavy" whole-warp threshold of the CTA kernel, "sim_g" lane-group width of the round loop (8, 16, 32),
+ * "fit_heavy" whole-warp threshold of the CTA kernel, "sim_g" lane-group width of the round loop (4, 8, 16, 32), "sim_cat_smem" 0 = catalog read from global memory,
  * "bidfit_wide" 0/1.  They choose between implementations of the same function (the reference has one:
  * BidderAllocation.py:29-65, Auction.py:28-74, Bidder.py:210-615); unknown names are AGYM_ERR_INVALID. */
 int agym_set_option(agym_handle* h, const char* name, double value);

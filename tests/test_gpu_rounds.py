@@ -54,10 +54,10 @@ def test_replay_fp64_matches_oracle_and_reference(name):
     eng.close()
 
 
-@pytest.mark.parametrize("G", ["8", "16", "32"])
+@pytest.mark.parametrize("G", ["4", "8", "16", "32"])
 @pytest.mark.parametrize("name", ["rounds_sp_ts_64x64", "rounds_sp_oracle_64x64", "rounds_fp_pA", "rounds_sp_ragged", "rounds_fp_search", "rounds_fp_bandit"])
 def test_replay_is_exact_for_every_lane_group_width(name, G):
-    """The launcher picks the lane-group width from the catalog width and the launch size (8 lanes for large launches);
+    """The launcher picks the lane-group width from the participants per round (sim_group_width; 4 to 32 lanes);
     every width must reproduce the reference's discrete decisions -- forced here through the "sim_g" option (agym_set_option)."""
     gu = _gpu()
     from auction_gym_b200 import _lib

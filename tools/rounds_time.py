@@ -11,6 +11,9 @@ A = I = 64; D, Do, P = 5, 4, 2
 E, V = ao.make_catalog(np.random.default_rng(0), A, I, D)
 for kind, name in ((1, "ts"), (0, "oracle")):
     eng = ag.Engine(R=R, A=A, I=I, D=D, Do=Do, P=P, mechanism=0, E=E, V=V, n_items=[I]*A, alloc_kind=[kind]*A, bidder_kind=[0]*A, precision=_lib.FP32, rounds_capacity=T)
+    import os
+    if os.environ.get('SIM_G'): eng.set_option('sim_g', float(os.environ['SIM_G']))
+    for kv in filter(None, os.environ.get('SIM_OPTS', '').split(',')): eng.set_option(kv.split('=')[0], float(kv.split('=')[1]))
     if kind: eng.set_allocator_state(torch.randn(R, A, I, Do+1, generator=torch.Generator().manual_seed(0)))
     ts = []
     for it in range(6):
