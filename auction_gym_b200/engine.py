@@ -430,21 +430,6 @@ class Engine:
         self.gathered_acc = torch.empty((self.comm_world, self.R, self.A, _lib.NUM_METRICS), dtype=torch.float64, device=self.device)
         self.gathered_revenue = torch.empty((self.comm_world, self.R), dtype=torch.float64, device=self.device)
 
-    def swap_metrics(self):
-        """Double-buffered accumulators: bind the spare (acc, revenue) pair for the next iteration and return the pair that
-        holds the iteration just finished, so that its read-out (copy to the host, all-gather) can run on another stream
-        while the next iteration computes.  The caller orders the reuse of a pair after its read-out (events).  Not with log
-        retention, whose accumulators carry over between iterations."""
-        if self.retention:
-            raise AgymError("swap_metrics: not available with log retention (the accumulators carry retained records)")
-        done = (self.acc, self.revenue)
-        if getattr(self, "_spare_metrics", None) is None:
-            self._spare_metrics = (torch.zeros_like(self.acc), torch.zeros_like(self.revenue))
-        self.acc, self.revenue = self._spare_metrics
-        self._spare_metrics = done
-        self._check(self.lib.agym_bind_metrics(self.handle, _ptr(self.acc), _ptr(self.revenue)))
-        return done
-
     def gather_metrics(self):
         """All-gather of every rank's accumulator block and revenue (agym_gather_metrics_nccl) on the current stream:
         returns device tensors [world, R, A, NUM_METRICS] and [world, R]."""
