@@ -386,8 +386,11 @@ def main():
                 read_out(sb, slot=(it - args.warmup) if timed else None)
 
     def step_e2e(it):
-        """The same iteration through the public API with HOST buffers: learnt state up, metrics + state down."""
+        """The same iteration through the public API with HOST buffers: learnt state up, metrics + state down.  A sub-shard's runs
+        start their next step only when their previous step's state and metrics ARE on the host (host-side synchronize of that
+        sub-shard's stream); the other sub-shards, whose runs are independent, keep the GPU busy meanwhile."""
         for sb in subs:
+            sb.stream.synchronize()
             with torch.cuda.stream(sb.stream):
                 e = sb.eng
                 if learnt:
@@ -400,8 +403,6 @@ def main():
                     sb.q_host.copy_(e.q, non_blocking=True)
                     sb.mp_host.copy_(e.m_prev, non_blocking=True)
                 read_out(sb, slot=(it - args.warmup) if it >= args.warmup else None)
-        for sb in subs:  # the step's result is on the host before the next step starts
-            sb.stream.synchronize()
 
     def join_streams():
         for sb in subs:
@@ -674,7 +675,8 @@ def main():
                 "fit_epochs_mean": fit_epochs_mean,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                         "note": "same iterations of the same trajectory as `value` (restart from the initial host state, same warm-up); every step "
-                                "uploads the learnt state from pinned host memory and reads state + metrics back"},
+                                "uploads the learnt state from pinned host memory and reads state + metrics back; a sub-shard's runs wait on the host "
+                                "for their own previous step's read-back, not for the other sub-shards'"},
                 "gpu_launches": int(launches), "gpu_launches_note": "agym_launch_count difference over the timed region on rank 0 (sim_kernel, bucket_kernel, "
                                                                      "fit_classify_kernel, fit_order_kernel, two fit_warp_kernel instantiations, pack_state_kernel per step and sub-shard)",
                 "subshards": NS,
