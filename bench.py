@@ -8,12 +8,16 @@ each: STRONG scaling, the whole job is fixed), T = 10 000 rounds per iteration, 
 P = 2, SecondPrice + TruthfulBidder + learnt Thompson-sampling allocator.  `--runs-per-gpu R` switches to weak scaling.
 One step = one iteration of every resident run = T rounds of the fused round-loop kernel (K1-K5) + the per-iteration
 allocator fits (K6, adam_ref: the reference's Adam + plateau scheduler + early-stop state machine) + the per-iteration
-metric read-out (+ at N > 1 the all-gather of the metric block, K8).  value = runs * T / step time (max over ranks).
+metric read-out to the host; at N > 1 the timed region ends with ONE NCCL all-gather of its iterations' metric blocks (K8:
+main.py:186-222 assembles its per-run rows once the runs have finished).  value = runs * T / step time (max over ranks).
+Each GPU processes its runs as 4 independent sub-shards on 4 CUDA streams (the tail of one sub-shard's fit grid, and end to
+end its PCIe copies, are covered by the others' kernels; runs are independent, results do not depend on the split).
 The timed steps are iterations W .. W+K-1 of ONE learning trajectory that starts from m ~ N(0, 1), q = 1: the fit gets
 cheaper as the allocators learn, so the iteration range is part of the configuration and is printed.
 
 The JSON line also carries: e2e (same iterations through the public API with the learnt state and metrics crossing PCIe
-from / to pinned host memory every step), fit_epochs_mean, full_workload (the whole N = 100-iteration trajectory),
+from / to pinned host memory every step; a sub-shard's next step waits on the host for its own read-back), fit_epochs_mean,
+full_workload (the whole N = 100-iteration trajectory), opt_in_newton_mode (the same under AGYM_FIT_NEWTON: a different algorithm),
 roofline (dominant kernel) + roofline_kernels (every kernel, incl. the staged resolution kernel K4 the north star puts
 the HBM bar on), cpu_baseline, clocks, gpu_launches (counted by the library).
 
