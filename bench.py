@@ -178,26 +178,32 @@ def measured_peaks():
 def profile_numbers(kernel_pattern, grid=None):
     """Counters of the newest committed ncu summary (profiles/r*_ncu_full.txt, written by tools/ncu_summary.py) whose kernel
     name matches; nothing here is a constant of this file.  `traffic` only when the capture's grid equals this run's."""
-    best = None
+    best, best_grid = None, None  # newest capture of the kernel; newest one whose grid equals this run's, if any
+
+    def consider(path, block):
+        nonlocal best, best_grid
+        if block.get("name") and re.search(kernel_pattern, block["name"]):
+            best = (path, block)
+            if grid is not None and block.get("launch__grid_size") == grid:
+                best_grid = (path, block)
+
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full.txt"))):
         block = {}
         for ln in open(path):
             if ln.startswith("Kernel Name"):
-                if block.get("name") and re.search(kernel_pattern, block["name"]):
-                    best = (path, block)
+                consider(path, block)
                 block = {"name": ln[len("Kernel Name"):].strip()}
                 continue
             f = ln.split()
             if len(f) >= 2 and not ln.startswith("-"):
                 try:
-                    block[f[0]] = float(f[1])
+                    block[f[0]] = float(f[1]) * ({"Gbyte": 1e3, "Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6}.get(f[2], 1.0) if len(f) > 2 else 1.0)
                 except ValueError:
                     pass
-        if block.get("name") and re.search(kernel_pattern, block["name"]):
-            best = (path, block)
+        consider(path, block)
     if best is None:
         return None
-    path, b = best
+    path, b = best_grid or best
     out = {"source": os.path.relpath(path, ROOT), "kernel": b["name"],
            "warp_instructions_per_sm_cycle": b.get("sm__inst_executed.avg.per_cycle_elapsed"),
            "issue_slots_active_pct": b.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
@@ -604,11 +610,12 @@ def main():
                 ts.append(s.elapsed_time(e))
             ms4 = float(np.mean(ts))
             by = Rk * T * ((13 * P + 10) if accumulate else (8 * P + 10))
-            prof = profile_numbers(r"k4_kernel_p2_acc" if accumulate else r"k4_kernel_p2\b", None)
+            k4_grid = Rk * ((T + 2047) // 2048) if accumulate else (Rk * T // 4 + 255) // 256  # csrc/agym_staged.cu launch_k4
+            prof = profile_numbers(r"k4_kernel_p2_acc" if accumulate else r"k4_kernel_p2\b", k4_grid)
             aux["k4_resolve" + ("+accumulate" if accumulate else "")] = {
                 "bound": "hbm", "achieved": by / ms4 / 1e6, "peak": peak, "unit": "GB/s", "frac": by / ms4 / 1e6 / peak,
                 "ms": ms4, "algorithmic_bytes": by, "opportunities_per_s": Rk * T / ms4 * 1e3,
-                "traffic": prof["dram_bytes"] if prof else None, "from_profile": prof,
+                "traffic": prof["dram_bytes"] if prof and prof.get("traffic_matches_this_grid") else None, "from_profile": prof,
                 "bytes_per_opportunity": (13 * P + 10) if accumulate else (8 * P + 10),
                 "note": f"{Rk * T} opportunities, {by / 1e6:.0f} MB algorithmic; L2 flushed (512 MB fill) before every timed launch; outside the timed step"}
         del b, flush
