@@ -111,6 +111,34 @@ def test_learning_config_improves_over_iterations(tmp_path):
     assert np.isfinite(m[..., :7]).all()
 
 
+@pytest.mark.parametrize("over", [{}, {"memory": 3000}, {"max_slots": 2}])
+def test_opt_in_newton_mode_through_the_driver(tmp_path, over):
+    """`run_experiment(fit_mode="newton")` / `main.py --fit-mode newton`: the opt-in regularised Newton allocator fit (NOT the
+    reference's algorithm, csrc/agym_fit_newton.cu) learns on the shipped config -- also on retained logs (`memory`) and with
+    several slots per round, where its rows are simply more rows -- and the default stays the reference's Adam trajectory."""
+    _need_gpu()
+    import auction_gym_b200 as ag
+
+    cfg = json.load(open(os.path.join(ROOT, "config", "SP_Truthful_TS.json")))
+    if "memory" in over:
+        for ac in cfg["agents"]:
+            ac["memory"] = over["memory"]
+    if "max_slots" in over:
+        cfg["max_slots"] = over["max_slots"]
+    cfg.update(num_runs=8, num_iter=4, rounds_per_iter=3000, output_dir=str(tmp_path) + "/o/")
+    path = str(tmp_path / "cfg.json")
+    json.dump(cfg, open(path, "w"))
+    nw = ag.run_experiment(path, fit_mode="newton")["metrics"]
+    assert np.isfinite(nw[..., :7]).all()
+    rmse = nw[..., 6].mean(axis=(0, 2))
+    welfare = nw[..., 1].sum(axis=2).mean(axis=0)
+    assert rmse[-1] < 0.8 * rmse[0] and welfare[-1] > 1.5 * welfare[0], (rmse, welfare)  # with `memory` the RMSE getter also covers kept records
+    if not over:
+        ref = ag.run_experiment(path)["metrics"]  # default fit mode: same first iteration (no fit yet), a different trajectory after it
+        np.testing.assert_allclose(nw[:, 0], ref[:, 0], rtol=1e-12, atol=1e-12)
+        assert not np.allclose(nw[:, 2], ref[:, 2])
+
+
 def test_memory_config_retains_logs_across_iterations(tmp_path):
     """`memory` in an agent's config (main.py:87, Agent.py:124-129): the getters sum over kept + new records, so the
     allocation regret reported per iteration (a sum of non-negative terms) covers several iterations' rounds, and the
