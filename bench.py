@@ -438,9 +438,19 @@ def main():
         torch.cuda.synchronize(dev)
         barrier()
         ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+        rank_ms.append(per_rank(ms))
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
+
+    rank_ms = []  # per timed region: every rank's own time (the reported time is their maximum)
+
+    def per_rank(ms):
+        if world == 1:
+            return [round(float(ms.item()), 3)]
+        allr = [torch.zeros_like(ms) for _ in range(world)]
+        dist.all_gather(allr, ms)
+        return [round(float(x.item()), 3) for x in allr]
 
     def reset_state():
         torch.cuda.synchronize(dev)
@@ -518,6 +528,7 @@ def main():
         torch.cuda.synchronize(dev)
         barrier()
         ms_full = torch.tensor([s_all.elapsed_time(e_all)], dtype=torch.float64, device=dev)
+        ms_ranks = per_rank(ms_full)
         if world > 1:
             dist.all_reduce(ms_full, op=dist.ReduceOp.MAX)
         ms_full = float(ms_full.item())
@@ -532,7 +543,7 @@ def main():
                 "value": runs_job * T * n_full / (ms_full * 1e-3), "unit": UNIT,
                 "ms_per_iteration": [round(a.elapsed_time(b), 3) for a, b in per_it],  # on sub-shard 0's stream
                 "fit_epochs_mean_per_iteration": [round(x, 1) for x in ep] if ep else None,
-                "welfare_last_iteration_per_run": welfare}
+                "welfare_last_iteration_per_run": welfare, "ms_per_rank": ms_ranks}
 
     # ---- the whole trajectory: N = 100 iterations from the initial state ----
     full, newton = None, None
@@ -684,6 +695,9 @@ def main():
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(args, world, runs_job, scaling, args.warmup, args.steps),
                 "fit_epochs_mean": fit_epochs_mean,
+                "ms_per_rank": {"value_region": rank_ms[0] if rank_ms else None, "e2e_region": rank_ms[1] if len(rank_ms) > 1 else None,
+                                "note": "each rank's own time for the timed region, its closing all-gather included (the collective aligns the ranks, so "
+                                        "the spread that is left is what happens after it); the reported time is the maximum"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                         "note": "same iterations of the same trajectory as `value` (restart from the initial host state, same warm-up); every step "
                                 "uploads the learnt state from pinned host memory and reads state + metrics back; a sub-shard's runs wait on the host "
