@@ -170,3 +170,34 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert d["port"]["kind"] == "port" and abs(d["port"]["fit_epochs"] / d["fit_epochs_mean"] - 1) < 0.05
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_bench_reads_its_profile_numbers_from_the_committed_captures(tmp_path, monkeypatch):
+    """bench.py prints no constants: the `from_profile` counters come from profiles/r*_ncu_full.txt at run time, from the newest
+    capture of the kernel -- of the SAME GRID when there is one (only then is `traffic` reported) -- with ncu's units honoured."""
+    import bench
+
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    (prof / "r9_x_ncu_full.txt").write_text(
+        "-" * 20 + "\n"
+        "Kernel Name    void k4_kernel_p2_acc<2, 5>(SimParams)\n"
+        "launch__grid_size    2560\n"
+        "launch__registers_per_thread    48 register/thread\n"
+        "dram__bytes_read.sum    100.5 Mbyte\n"
+        "dram__bytes_write.sum    50 Mbyte\n"
+        "smsp__issue_active.avg.pct_of_peak_sustained_active    58.6 %\n"
+        + "-" * 20 + "\n"
+        "Kernel Name    void k4_kernel_p2_acc<2, 5>(SimParams)\n"
+        "launch__grid_size    20480\n"
+        "dram__bytes_read.sum    1.09 Gbyte\n"
+        "dram__bytes_write.sum    433 Mbyte\n")
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    small = bench.profile_numbers(r"k4_kernel_p2_acc", 2560)
+    assert small["traffic_matches_this_grid"] and abs(small["dram_bytes"] - 150.5e6) < 1 and small["registers_per_thread"] == 48
+    assert small["issue_slots_active_pct"] == 58.6 and small["source"].endswith("r9_x_ncu_full.txt")
+    big = bench.profile_numbers(r"k4_kernel_p2_acc", 20480)
+    assert big["traffic_matches_this_grid"] and abs(big["dram_bytes"] - 1.523e9) < 1e3
+    other = bench.profile_numbers(r"k4_kernel_p2_acc", 777)  # no capture of that grid: the newest one, flagged
+    assert other["grid"] == 20480 and not other["traffic_matches_this_grid"]
+    assert bench.profile_numbers(r"no_such_kernel", None) is None
